@@ -1,0 +1,13 @@
+"""Import shim: the package directory is named `multi-spectrogram-viewer_b200` (not a valid Python
+identifier), so it is loaded from its path and published as the module `msv_b200`."""
+import importlib.util
+import os
+import sys
+
+_pkg_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi-spectrogram-viewer_b200")
+_spec = importlib.util.spec_from_file_location(
+    "msv_b200", os.path.join(_pkg_dir, "__init__.py"), submodule_search_locations=[_pkg_dir]
+)
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["msv_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,470 @@
+// capi.cpp -- the extern "C" boundary declared in include/sgx.h.  Every entry point catches all
+// exceptions and maps them to a status + thread-local message; nothing unwinds across the ABI.
+#include <cstring>
+#include <string>
+
+#include "engine.h"
+
+using namespace sgx;
+
+static thread_local std::string g_last_error;
+
+struct sgx_multitrack {
+    MultiTrack impl;
+    sgx_multitrack(const sgx_settings &s, int dev, cudaStream_t st) : impl(s, dev, st) {}
+};
+
+template <class F> static int guarded(F &&f)
+{
+    try {
+        f();
+        return SGX_OK;
+    } catch (const Error &e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        g_last_error = "out of host memory";
+        return SGX_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return SGX_ERR_STATE;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return SGX_ERR_STATE;
+    }
+}
+
+#define REQUIRE(cond, msg) do { if (!(cond)) throw Error(SGX_ERR_BAD_ARG, msg); } while (0)
+
+extern "C" {
+
+const char *sgx_last_error(void) { return g_last_error.c_str(); }
+
+int sgx_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem)
+{
+    return guarded([&] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0) { cudaGetLastError(); throw Error(SGX_ERR_CUDA, "no usable CUDA device"); }
+        REQUIRE(device >= 0 && device < count, "device ordinal out of range");
+        cudaDeviceProp p{};
+        SGX_CUDA(cudaGetDeviceProperties(&p, device));
+        if (sm_count) *sm_count = p.multiProcessorCount;
+        if (cc_major) *cc_major = p.major;
+        if (cc_minor) *cc_minor = p.minor;
+        if (total_mem) *total_mem = p.totalGlobalMem;
+    });
+}
+
+uint64_t sgx_kernel_launch_count(void) { return launch_count(); }
+
+void sgx_settings_default(sgx_settings *s)
+{
+    if (!s) return;
+    std::memset(s, 0, sizeof(*s));
+    s->win_ms = 40.0f; s->t_overlap = 4; s->f_overlap = 1; s->freq_scale = SGX_FREQ_MEL; s->db_range = 120.0f;
+}
+
+int sgx_mt_new(sgx_multitrack **out) { return sgx_mt_new_ex(nullptr, 0, nullptr, out); }
+
+int sgx_mt_new_ex(const sgx_settings *settings, int device, void *cuda_stream, sgx_multitrack **out)
+{
+    return guarded([&] {
+        REQUIRE(out, "out is NULL");
+        *out = nullptr;
+        sgx_settings s;
+        if (settings) s = *settings; else sgx_settings_default(&s);
+        REQUIRE(s.freq_scale == SGX_FREQ_LINEAR || s.freq_scale == SGX_FREQ_MEL, "freq_scale");
+        *out = new sgx_multitrack(s, device, static_cast<cudaStream_t>(cuda_stream));
+    });
+}
+
+void sgx_mt_free(sgx_multitrack *mt)
+{
+    guarded([&] { delete mt; });
+}
+
+static int add_generic(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, const void *const *pcm, int fmt,
+                       const size_t *n_samples, const uint32_t *sr, const uint32_t *channels, bool on_device,
+                       int *changed)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        REQUIRE(n_ids == 0 || (id_list && pcm && n_samples && sr && channels), "NULL argument");
+        std::vector<size_t> ids(id_list, id_list + n_ids);
+        std::vector<PcmSource> srcs(n_ids);
+        for (size_t i = 0; i < n_ids; ++i)
+            srcs[i] = PcmSource{pcm[i], fmt, n_samples[i], sr[i], channels[i], on_device, std::string()};
+        const bool c = mt->impl.add_tracks(ids, srcs, changed != nullptr || !on_device);
+        if (changed) *changed = c ? 1 : 0;
+    });
+}
+
+int sgx_mt_add_tracks_pcm(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, const float *const *pcm,
+                          const size_t *n_samples, const uint32_t *sr, const uint32_t *channels, int *changed)
+{
+    return add_generic(mt, id_list, n_ids, reinterpret_cast<const void *const *>(pcm), PCM_F32, n_samples, sr,
+                       channels, false, changed);
+}
+
+int sgx_mt_add_tracks_pcm_i16(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, const int16_t *const *pcm,
+                              const size_t *n_samples, const uint32_t *sr, const uint32_t *channels, int *changed)
+{
+    return add_generic(mt, id_list, n_ids, reinterpret_cast<const void *const *>(pcm), PCM_I16, n_samples, sr,
+                       channels, false, changed);
+}
+
+int sgx_mt_add_tracks_pcm_device(sgx_multitrack *mt, const size_t *id_list, size_t n_ids,
+                                 const float *const *d_pcm, const size_t *n_samples, const uint32_t *sr,
+                                 const uint32_t *channels, int *changed)
+{
+    return add_generic(mt, id_list, n_ids, reinterpret_cast<const void *const *>(d_pcm), PCM_F32, n_samples, sr,
+                       channels, true, changed);
+}
+
+int sgx_mt_add_tracks(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, const char *path_list, int *changed)
+{
+    return guarded([&] {
+        REQUIRE(mt && path_list && (id_list || n_ids == 0), "NULL argument");
+        // lib.rs:173: ids zipped with path_list.split("\n")
+        std::vector<std::string> paths;
+        const char *p = path_list;
+        for (;;) {
+            const char *nl = std::strchr(p, '\n');
+            paths.emplace_back(nl ? std::string(p, nl) : std::string(p));
+            if (!nl) break;
+            p = nl + 1;
+        }
+        const size_t n = std::min(n_ids, paths.size()); // zip stops at the shorter
+        std::vector<WavData> wavs(n);
+        for (size_t i = 0; i < n; ++i) wavs[i] = read_wav(paths[i]);
+        std::vector<size_t> ids(id_list, id_list + n);
+        std::vector<PcmSource> srcs(n);
+        for (size_t i = 0; i < n; ++i) {
+            const WavData &w = wavs[i];
+            srcs[i] = PcmSource{w.is_i16 ? (const void *)w.i16.data() : (const void *)w.f32.data(),
+                                w.is_i16 ? PCM_I16 : PCM_F32, w.n, w.sr, w.ch, false, paths[i]};
+        }
+        const bool c = mt->impl.add_tracks(ids, srcs, true);
+        if (changed) *changed = c ? 1 : 0;
+    });
+}
+
+int sgx_mt_remove_track(sgx_multitrack *mt, size_t id, int *changed)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        const bool c = mt->impl.remove_track(id, changed != nullptr);
+        if (changed) *changed = c ? 1 : 0;
+    });
+}
+
+static int spec_image_host(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t nheight, int channels,
+                           uint8_t *out, size_t cap, size_t *written)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        const size_t need = (size_t)mt->impl.image_width(id, px_per_sec) * nheight * channels;
+        if (written) *written = need;
+        if (!out) return;
+        if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+        std::vector<uint8_t> img = mt->impl.render_host(id, px_per_sec, nheight, channels);
+        if (!img.empty()) std::memcpy(out, img.data(), img.size());
+    });
+}
+
+int sgx_mt_get_spec_image(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t nheight, uint8_t *out,
+                          size_t cap, size_t *written)
+{
+    return spec_image_host(mt, id, px_per_sec, nheight, 3, out, cap, written);
+}
+
+int sgx_mt_get_spec_image_rgba(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t nheight, uint8_t *out,
+                               size_t cap, size_t *written)
+{
+    return spec_image_host(mt, id, px_per_sec, nheight, 4, out, cap, written);
+}
+
+int sgx_mt_get_spec_image_device(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t nheight, int channels,
+                                 uint8_t *d_out, size_t cap, size_t *written)
+{
+    uint8_t *outs[1] = {d_out};
+    size_t caps[1] = {cap};
+    return sgx_mt_get_spec_images_device(mt, &id, 1, px_per_sec, nheight, channels, outs, caps, written);
+}
+
+int sgx_mt_get_spec_images_device(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, float px_per_sec,
+                                  uint32_t nheight, int channels, uint8_t *const *d_out, const size_t *cap,
+                                  size_t *written)
+{
+    return guarded([&] {
+        REQUIRE(mt && (id_list || n_ids == 0), "NULL argument");
+        REQUIRE(!d_out || cap, "cap is NULL");
+        std::vector<size_t> ids(id_list, id_list + n_ids);
+        mt->impl.render(ids, px_per_sec, nheight, channels, d_out, cap, written);
+    });
+}
+
+int sgx_mt_get_wav_image(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t nheight, float amp_min,
+                         float amp_max, uint8_t *out, size_t cap, size_t *written)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        const size_t need = (size_t)mt->impl.image_width(id, px_per_sec) * nheight * 4;
+        if (written) *written = need;
+        if (!out) return;
+        if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+        std::vector<uint8_t> img = mt->impl.wav_image(id, px_per_sec, nheight, amp_min, amp_max);
+        if (!img.empty()) std::memcpy(out, img.data(), img.size());
+    });
+}
+
+int sgx_mt_get_frequency_hz(sgx_multitrack *mt, size_t id, float relative_freq, float *out)
+{
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.frequency_hz(id, relative_freq); });
+}
+int sgx_mt_get_max_db(sgx_multitrack *mt, float *out)
+{
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.max_db(); });
+}
+int sgx_mt_get_min_db(sgx_multitrack *mt, float *out)
+{
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.min_db(); });
+}
+int sgx_mt_get_max_sec(sgx_multitrack *mt, float *out)
+{
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.max_sec(); });
+}
+int sgx_mt_get_sec(sgx_multitrack *mt, size_t id, float *out)
+{
+    return guarded([&] {
+        REQUIRE(mt && out, "NULL argument");
+        const Track &t = mt->impl.track(id);
+        *out = (float)t.n / (float)t.sr; // lib.rs:338
+    });
+}
+int sgx_mt_get_sr(sgx_multitrack *mt, size_t id, uint32_t *out)
+{
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.track(id).sr; });
+}
+
+static void copy_string(const std::string &s, char *out, size_t cap, size_t *written)
+{
+    if (written) *written = s.size() + 1;
+    if (!out) return;
+    if (cap < s.size() + 1) throw Error(SGX_ERR_BUFFER, "string buffer too small");
+    std::memcpy(out, s.c_str(), s.size() + 1);
+}
+int sgx_mt_get_path(sgx_multitrack *mt, size_t id, char *out, size_t cap, size_t *written)
+{
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); copy_string(mt->impl.track(id).path, out, cap, written); });
+}
+int sgx_mt_get_filename(sgx_multitrack *mt, size_t id, char *out, size_t cap, size_t *written)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        const std::string &p = mt->impl.track(id).path;
+        const size_t slash = p.find_last_of('/');
+        copy_string(slash == std::string::npos ? p : p.substr(slash + 1), out, cap, written);
+    });
+}
+
+int sgx_get_colormap(uint8_t out[30])
+{
+    static const uint8_t cm[30] = {0, 0, 4, 27, 12, 65, 74, 12, 107, 120, 28, 109, 165, 44, 96,
+                                   207, 68, 70, 237, 105, 37, 251, 155, 6, 247, 209, 61, 252, 255, 164};
+    if (!out) { g_last_error = "out is NULL"; return SGX_ERR_BAD_ARG; }
+    std::memcpy(out, cm, 30);
+    return SGX_OK;
+}
+
+int sgx_mt_get_spec_shape(sgx_multitrack *mt, size_t id, size_t *n_frames, size_t *n_out)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        const Track &t = mt->impl.track(id);
+        if (n_frames) *n_frames = t.n_frames;
+        if (n_out) *n_out = t.n_out;
+    });
+}
+
+int sgx_mt_get_spec_db(sgx_multitrack *mt, size_t id, float *out, size_t cap_elems, size_t *written_elems)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        const Track &t = mt->impl.track(id);
+        const size_t need = t.n_frames * t.n_out;
+        if (written_elems) *written_elems = need;
+        if (!out) return;
+        if (cap_elems < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+        SGX_CUDA(cudaMemcpyAsync(out, t.spec.p, need * sizeof(float), cudaMemcpyDeviceToHost, mt->impl.stream()));
+        SGX_CUDA(cudaStreamSynchronize(mt->impl.stream()));
+    });
+}
+
+int sgx_mt_get_image_width(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t *nwidth)
+{
+    return guarded([&] { REQUIRE(mt && nwidth, "NULL argument"); *nwidth = mt->impl.image_width(id, px_per_sec); });
+}
+
+int sgx_mt_range_device_ptr(sgx_multitrack *mt, float **d_max_negmin)
+{
+    return guarded([&] { REQUIRE(mt && d_max_negmin, "NULL argument"); *d_max_negmin = mt->impl.range_device_ptr(); });
+}
+int sgx_mt_commit_range_device(sgx_multitrack *mt)
+{
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->impl.commit_range_device(); });
+}
+int sgx_mt_set_global_max_sr(sgx_multitrack *mt, uint32_t max_sr)
+{
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->impl.set_global_max_sr(max_sr); });
+}
+int sgx_mt_synchronize(sgx_multitrack *mt, int *changed)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        const bool c = mt->impl.synchronize();
+        if (changed) *changed = c ? 1 : 0;
+    });
+}
+
+// ---- surface 2 ------------------------------------------------------------------------------------------
+size_t sgx_calc_proper_n_fft(size_t win_length) { return calc_proper_n_fft(win_length); }
+
+int sgx_track_params(uint32_t sr, const sgx_settings *s, size_t *win_length, size_t *hop_length, size_t *n_fft)
+{
+    return guarded([&] {
+        REQUIRE(win_length && hop_length && n_fft, "NULL argument");
+        sgx_settings d;
+        if (s) d = *s; else sgx_settings_default(&d);
+        REQUIRE(d.t_overlap > 0 && d.f_overlap > 0, "overlap factors must be positive");
+        const float w0 = d.win_ms * (float)sr / 1000.0f;
+        size_t h = (size_t)std::round(w0 / (float)d.t_overlap);
+        if (d.hop_length) h = d.hop_length;
+        size_t w = h * d.t_overlap;
+        if (d.win_length) w = d.win_length;
+        size_t f = calc_proper_n_fft(w) * d.f_overlap;
+        if (d.n_fft) f = d.n_fft;
+        *win_length = w; *hop_length = h; *n_fft = f;
+    });
+}
+
+int sgx_hann(size_t size, int symmetric, float *out)
+{
+    return guarded([&] { REQUIRE(out || size == 0, "out is NULL"); hann(size, symmetric != 0, out); });
+}
+int sgx_calc_window(size_t win_length, size_t n_fft, float *out)
+{
+    return guarded([&] { REQUIRE(out || win_length == 0, "out is NULL"); calc_window(win_length, n_fft, out); });
+}
+float sgx_hz_to_mel(float hz) { return hz_to_mel(hz); }
+float sgx_mel_to_hz(float mel) { return mel_to_hz(mel); }
+
+int sgx_calc_mel_fb(uint32_t sr, size_t n_fft, size_t n_mel, float fmin, float fmax, int do_norm, float *out)
+{
+    return guarded([&] {
+        REQUIRE(out, "out is NULL");
+        REQUIRE(n_fft % 2 == 0, "n_fft must be even (mel.rs:50)");
+        REQUIRE(n_mel != 0, "n_mel must not be 0 (mel.rs:51)");
+        calc_mel_fb(sr, n_fft, n_mel, fmin, fmax, do_norm != 0, out);
+    });
+}
+
+int sgx_calc_mel_fb_default(uint32_t sr, size_t n_fft, float *out, size_t cap_elems, size_t *n_mel)
+{
+    return guarded([&] {
+        REQUIRE(n_mel, "n_mel is NULL");
+        REQUIRE(n_fft % 2 == 0 && n_fft >= 2, "n_fft must be even (mel.rs:50)");
+        std::vector<float> fb;
+        *n_mel = calc_mel_fb_default(sr, n_fft, fb);
+        if (out) {
+            if (cap_elems < fb.size()) throw Error(SGX_ERR_BUFFER, "filterbank buffer too small");
+            std::memcpy(out, fb.data(), fb.size() * sizeof(float));
+        }
+    });
+}
+
+long sgx_stft_num_frames(size_t n, size_t win_length, size_t hop_length)
+{
+    return stft_num_frames(n, win_length, hop_length);
+}
+
+static int stft_stage(int mode, const float *input, size_t n, size_t win, size_t hop, size_t n_fft,
+                      const float *window, const float *mel_fb, size_t n_mel, float *out, size_t cap,
+                      size_t *n_frames)
+{
+    return guarded([&] {
+        REQUIRE(input, "input is NULL");
+        const StageOut so = stage_stft(mode, input, n, win, hop, n_fft, window, mel_fb, n_mel, out, cap);
+        if (n_frames) *n_frames = so.n_frames;
+    });
+}
+
+int sgx_perform_stft(const float *input, size_t n, size_t win_length, size_t hop_length, size_t n_fft,
+                     const float *window, float *out, size_t cap_elems, size_t *n_frames)
+{
+    return stft_stage(MODE_COMPLEX, input, n, win_length, hop_length, n_fft, window, nullptr, 0, out, cap_elems, n_frames);
+}
+int sgx_stft_magnitude(const float *input, size_t n, size_t win_length, size_t hop_length, size_t n_fft,
+                       const float *window, float *out, size_t cap_elems, size_t *n_frames)
+{
+    return stft_stage(MODE_MAG, input, n, win_length, hop_length, n_fft, window, nullptr, 0, out, cap_elems, n_frames);
+}
+int sgx_melspectrogram_db(const float *input, size_t n, size_t win_length, size_t hop_length, size_t n_fft,
+                          const float *window, const float *mel_fb, size_t n_mel, float *out, size_t cap_elems,
+                          size_t *n_frames)
+{
+    return stft_stage(mel_fb ? MODE_MEL_DB : MODE_LIN_DB, input, n, win_length, hop_length, n_fft, window, mel_fb,
+                      n_mel, out, cap_elems, n_frames);
+}
+
+int sgx_amp_to_db_default(float *x, size_t n)
+{
+    return guarded([&] { REQUIRE(x || n == 0, "x is NULL"); stage_amp_to_db(x, n); });
+}
+
+int sgx_spec_to_grey(const float *spec, size_t n_frames, size_t n_out, float up_ratio, float max_db, float min_db,
+                     float *grey, size_t cap_elems, uint32_t *height)
+{
+    return guarded([&] {
+        REQUIRE(spec || !grey, "spec is NULL");
+        const uint32_t h = stage_spec_to_grey(spec, n_frames, n_out, up_ratio, max_db, min_db, grey, cap_elems);
+        if (height) *height = h;
+    });
+}
+
+int sgx_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint32_t nwidth, uint32_t nheight,
+                    int channels, uint8_t *out, size_t cap)
+{
+    return guarded([&] {
+        REQUIRE(grey && out, "NULL argument");
+        stage_grey_to_rgb(grey, width, height, nwidth, nheight, channels, out, cap);
+    });
+}
+
+int sgx_wav_to_image(const float *wav, size_t n, uint32_t nwidth, uint32_t nheight, float amp_min, float amp_max,
+                     uint8_t *out, size_t cap)
+{
+    return guarded([&] {
+        REQUIRE(wav && out, "NULL argument");
+        stage_wav_to_image(wav, n, nwidth, nheight, amp_min, amp_max, out, cap);
+    });
+}
+
+int sgx_open_wav(const char *path, float *out, size_t cap_elems, size_t *n_samples, uint32_t *channels, uint32_t *sr)
+{
+    return guarded([&] {
+        REQUIRE(path, "path is NULL");
+        const WavData w = read_wav(path);
+        if (n_samples) *n_samples = w.n;
+        if (channels) *channels = w.ch;
+        if (sr) *sr = w.sr;
+        if (!out) return;
+        const size_t total = w.n * w.ch;
+        if (cap_elems < total) throw Error(SGX_ERR_BUFFER, "sample buffer too small");
+        if (w.is_i16) for (size_t i = 0; i < total; ++i) out[i] = (float)w.i16[i] / 32768.0f; // audio.rs:16-19
+        else std::memcpy(out, w.f32.data(), total * sizeof(float));
+    });
+}
+
+} // extern "C"

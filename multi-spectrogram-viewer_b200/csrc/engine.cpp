@@ -1,0 +1,641 @@
+// engine.cpp -- host orchestration above the kernels (no arithmetic of the path happens here
+// except the once-per-sample-rate tables of host_tables.cpp).
+#include "engine.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace sgx {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+void cuda_check(cudaError_t e, const char *what, const char *file, int line)
+{
+    if (e == cudaSuccess) return;
+    cudaGetLastError(); // clear the sticky non-fatal error state
+    const char *base = std::strrchr(file, '/');
+    throw Error(SGX_ERR_CUDA, std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " in " +
+                                  what + " (" + (base ? base + 1 : file) + ":" + std::to_string(line) + ")");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DeviceCtx
+// ---------------------------------------------------------------------------------------------------
+static std::mutex g_ctx_mutex;
+static std::map<int, std::unique_ptr<DeviceCtx>> g_ctx;
+
+DeviceCtx::DeviceCtx(int d) : device_(d)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        throw Error(SGX_ERR_CUDA, "no usable CUDA device (this engine has no CPU path)");
+    }
+    if (d < 0 || d >= count) throw Error(SGX_ERR_BAD_ARG, "CUDA device ordinal out of range");
+    cudaDeviceProp prop{};
+    SGX_CUDA(cudaGetDeviceProperties(&prop, d));
+    if (prop.major < 10)
+        throw Error(SGX_ERR_CUDA, std::string("kernels are built for sm_100a only; device is ") + prop.name);
+    sm_count = prop.multiProcessorCount;
+}
+
+DeviceCtx &DeviceCtx::get(int device)
+{
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    auto it = g_ctx.find(device);
+    if (it == g_ctx.end()) it = g_ctx.emplace(device, std::unique_ptr<DeviceCtx>(new DeviceCtx(device))).first;
+    return *it->second;
+}
+
+FftPlan &DeviceCtx::plan(size_t n_fft)
+{
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    auto it = plans_.find(n_fft);
+    if (it != plans_.end()) return *it->second;
+    std::unique_ptr<FftPlan> p(new FftPlan());
+    if (!stft_config_for(n_fft, &p->cfg))
+        throw Error(SGX_ERR_BAD_ARG, "n_fft must be a power of two in [2, 16384] (rustfft Radix4, realfft.rs:94)");
+    if (!p->cfg.generic) {
+        const int h = p->cfg.h;
+        std::vector<float2> tw(h), sp(h / 2 + 1);
+        make_fft_tables(h, tw.data(), sp.data());
+        p->tw.alloc(h); p->split.alloc(h / 2 + 1);
+        SGX_CUDA(cudaMemcpy(p->tw.p, tw.data(), sizeof(float2) * h, cudaMemcpyHostToDevice));
+        SGX_CUDA(cudaMemcpy(p->split.p, sp.data(), sizeof(float2) * (h / 2 + 1), cudaMemcpyHostToDevice));
+    }
+    it = plans_.emplace(n_fft, std::move(p)).first;
+    return *it->second;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shared helper: upload tables for one (win, n_fft, filterbank)
+// ---------------------------------------------------------------------------------------------------
+static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *window,
+                        const float *mel_fb, size_t n_mel, const StftConfig &cfg, cudaStream_t s)
+{
+    tt.win = win; tt.n_fft = n_fft; tt.n_mel = mel_fb ? n_mel : 0;
+    std::vector<float> wf(n_fft, 0.0f);
+    const size_t pad_l = (n_fft - win) / 2; // lib.rs:400
+    for (size_t j = 0; j < win; ++j) wf[pad_l + j] = window[j];
+    tt.win_f.upload(wf.data(), n_fft, s);
+    if (mel_fb) {
+        const int tpg = cfg.generic ? 1 : cfg.h / cfg.pts;
+        MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg);
+        if (cfg.generic) mb.log2_split = 0;
+        tt.mel_lo.upload(mb.lo.data(), mb.lo.size(), s);
+        tt.mel_cnt.upload(mb.cnt.data(), mb.cnt.size(), s);
+        tt.mel_off.upload(mb.off.data(), mb.off.size(), s);
+        tt.mel_w.upload(mb.w.data(), mb.w.size(), s);
+        tt.mel_log2p = mb.log2_split;
+    }
+    SGX_CUDA(cudaStreamSynchronize(s)); // host vectors die here
+}
+
+static StftTrack make_desc(const void *d_pcm, int fmt, size_t n, uint32_t ch, size_t win, size_t hop,
+                           size_t n_fft, size_t T, const TrackTables &tt, float *out, size_t n_out,
+                           unsigned *slot)
+{
+    StftTrack d{};
+    d.pcm = d_pcm; d.n = (long long)n; d.ch = (int)ch; d.fmt = fmt;
+    d.win = (int)win; d.hop = (int)hop; d.pad_l = (int)((n_fft - win) / 2);
+    d.n_frames = (int)T; d.win_f = tt.win_f.p; d.out = out; d.n_out = (int)n_out;
+    d.mel_lo = tt.mel_lo.p; d.mel_cnt = tt.mel_cnt.p; d.mel_off = tt.mel_off.p; d.mel_w = tt.mel_w.p;
+    d.mel_log2p = tt.mel_log2p; d.range_slot = slot; d.tile_begin = 0;
+    return d;
+}
+
+static void check_stft_args(size_t n, size_t win, size_t hop, size_t n_fft, long *T)
+{
+    if (n_fft < 2 || (n_fft & (n_fft - 1)) != 0 || n_fft > 16384)
+        throw Error(SGX_ERR_BAD_ARG, "n_fft must be a power of two in [2, 16384]");
+    if (win > n_fft) throw Error(SGX_ERR_BAD_ARG, "win_length > n_fft (usize underflow at lib.rs:400)");
+    if (hop > (size_t)1 << 24) throw Error(SGX_ERR_BAD_ARG, "hop_length too large");
+    *T = stft_num_frames(n, win, hop);
+    if (*T < 0)
+        throw Error(SGX_ERR_BAD_ARG, "input shorter than the window / reflect padding (the reference panics on its slices, lib.rs:412-433)");
+    if (*T > 0x7fffffffL / 2) throw Error(SGX_ERR_BAD_ARG, "too many frames");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MultiTrack
+// ---------------------------------------------------------------------------------------------------
+MultiTrack::MultiTrack(const sgx_settings &s, int device, cudaStream_t stream)
+    : set_(s), device_(device), stream_(stream), max_db_(-INFINITY), min_db_(INFINITY)
+{
+    if (!(s.win_ms > 0.0f) || s.t_overlap == 0 || s.f_overlap == 0)
+        throw Error(SGX_ERR_BAD_ARG, "settings: win_ms, t_overlap, f_overlap must be positive");
+    ctx_ = &DeviceCtx::get(device);
+    SGX_CUDA(cudaSetDevice(device));
+    if (!stream_) { SGX_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true; }
+    n_slots_ = 1024;
+    slots_.alloc((size_t)n_slots_ * 2);
+    SGX_CUDA(launch_range_init(slots_.p, n_slots_, stream_));
+    for (int i = n_slots_ - 1; i >= 0; --i) free_slots_.push_back(i);
+    d_local_.alloc(2); d_state_.alloc(4);
+    const float st[4] = {-INFINITY, INFINITY, 0.0f, 0.0f}; // lib.rs:104-105
+    const float lc[2] = {-INFINITY, -INFINITY};
+    SGX_CUDA(cudaMemcpyAsync(d_state_.p, st, sizeof(st), cudaMemcpyHostToDevice, stream_));
+    SGX_CUDA(cudaMemcpyAsync(d_local_.p, lc, sizeof(lc), cudaMemcpyHostToDevice, stream_));
+    SGX_CUDA(cudaStreamSynchronize(stream_));
+}
+
+MultiTrack::~MultiTrack()
+{
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    tracks_.clear(); tables_.clear(); axis_.clear();
+    if (own_stream_) cudaStreamDestroy(stream_);
+}
+
+void MultiTrack::derive_params(uint32_t sr, size_t *win, size_t *hop, size_t *n_fft) const
+{
+    // lib.rs:43-46
+    const float w0 = set_.win_ms * (float)sr / 1000.0f;
+    size_t h = (size_t)std::round(w0 / (float)set_.t_overlap);
+    if (set_.hop_length) h = set_.hop_length;
+    size_t w = h * set_.t_overlap;
+    if (set_.win_length) w = set_.win_length;
+    size_t f = calc_proper_n_fft(w) * set_.f_overlap;
+    if (set_.n_fft) f = set_.n_fft;
+    *win = w; *hop = h; *n_fft = f;
+}
+
+TrackTables *MultiTrack::tables_for(uint32_t sr, size_t win, size_t n_fft)
+{
+    const auto key = std::make_tuple(sr, win, n_fft, set_.n_mel);
+    auto it = tables_.find(key);
+    if (it != tables_.end()) return it->second.get();
+    std::unique_ptr<TrackTables> tt(new TrackTables());
+    std::vector<float> window(win);
+    calc_window(win, n_fft, window.data()); // lib.rs:138-140
+    std::vector<float> fb;
+    size_t n_mel = 0;
+    if (set_.freq_scale == SGX_FREQ_MEL) {
+        if (set_.n_mel) {
+            n_mel = set_.n_mel;
+            fb.assign((n_fft / 2 + 1) * n_mel, 0.0f);
+            calc_mel_fb(sr, n_fft, n_mel, 0.0f, -1.0f, true, fb.data());
+        } else {
+            n_mel = calc_mel_fb_default(sr, n_fft, fb); // lib.rs:151-158
+            if (n_mel == 0) throw Error(SGX_ERR_BAD_ARG, "default mel filterbank is empty for this sr / n_fft");
+        }
+    }
+    fill_tables(*tt, win, n_fft, window.data(), n_mel ? fb.data() : nullptr, n_mel, ctx_->plan(n_fft).cfg, stream_);
+    TrackTables *raw = tt.get();
+    tables_.emplace(key, std::move(tt));
+    return raw;
+}
+
+int MultiTrack::alloc_slot()
+{
+    if (free_slots_.empty()) {
+        // grow: new array, identity-initialised, old contents copied
+        const int nn = n_slots_ * 2;
+        DevBuf<unsigned> ns;
+        ns.alloc((size_t)nn * 2);
+        SGX_CUDA(launch_range_init(ns.p, nn, stream_));
+        SGX_CUDA(cudaMemcpyAsync(ns.p, slots_.p, sizeof(unsigned) * 2 * n_slots_, cudaMemcpyDeviceToDevice, stream_));
+        SGX_CUDA(cudaStreamSynchronize(stream_));
+        slots_ = std::move(ns);
+        for (int i = nn - 1; i >= n_slots_; --i) free_slots_.push_back(i);
+        n_slots_ = nn;
+    }
+    const int s = free_slots_.back();
+    free_slots_.pop_back();
+    return s;
+}
+
+void MultiTrack::drop_track(size_t id)
+{
+    auto it = tracks_.find(id);
+    if (it == tracks_.end()) return;
+    // buffers may still be in use by enqueued work
+    SGX_CUDA(cudaStreamSynchronize(stream_));
+    if (it->second.slot >= 0) {
+        SGX_CUDA(launch_range_init(slots_.p + 2 * it->second.slot, 1, stream_));
+        free_slots_.push_back(it->second.slot);
+    }
+    tracks_.erase(it);
+}
+
+void MultiTrack::reduce_and_commit(bool commit)
+{
+    SGX_CUDA(launch_range_reduce(slots_.p, n_slots_, d_local_.p, stream_));
+    // deferred mode: a multi-GPU driver all-reduces d_local_ first and commits afterwards
+    if (commit) { SGX_CUDA(launch_range_commit(d_local_.p, set_.db_range, d_state_.p, stream_)); pending_ = true; }
+}
+
+void MultiTrack::commit_range_device()
+{
+    SGX_CUDA(launch_range_commit(d_local_.p, set_.db_range, d_state_.p, stream_));
+    pending_ = true;
+}
+
+bool MultiTrack::synchronize()
+{
+    SGX_CUDA(cudaSetDevice(device_));
+    if (pending_) {
+        float st[4];
+        SGX_CUDA(cudaMemcpyAsync(st, d_state_.p, sizeof(st), cudaMemcpyDeviceToHost, stream_));
+        SGX_CUDA(cudaStreamSynchronize(stream_));
+        max_db_ = st[0]; min_db_ = st[1];
+        if (st[2] != 0.0f) {
+            changed_acc_ = true;
+            const float zero = 0.0f;
+            SGX_CUDA(cudaMemcpyAsync(d_state_.p + 2, &zero, sizeof(float), cudaMemcpyHostToDevice, stream_));
+            SGX_CUDA(cudaStreamSynchronize(stream_));
+        }
+        pending_ = false;
+    } else {
+        SGX_CUDA(cudaStreamSynchronize(stream_));
+    }
+    const bool c = changed_acc_;
+    changed_acc_ = false;
+    return c;
+}
+
+uint32_t MultiTrack::effective_max_sr() const { return global_max_sr_ ? std::max(global_max_sr_, max_sr_) : max_sr_; }
+
+bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs, bool want_changed)
+{
+    SGX_CUDA(cudaSetDevice(device_));
+    if (ids.size() != srcs.size()) throw Error(SGX_ERR_BAD_ARG, "id_list and track list differ in length");
+    // ---- validate everything before touching state (atomic, unlike lib.rs:174-189) -------------------
+    struct Pre { size_t win, hop, n_fft; long T; };
+    std::vector<Pre> pre(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        const PcmSource &s = srcs[i];
+        if (!s.data || s.n == 0 || s.ch == 0 || s.sr == 0) throw Error(SGX_ERR_BAD_ARG, "empty track");
+        derive_params(s.sr, &pre[i].win, &pre[i].hop, &pre[i].n_fft);
+        check_stft_args(s.n, pre[i].win, pre[i].hop, pre[i].n_fft, &pre[i].T);
+    }
+    // ---- insert tracks (lib.rs:174-187) --------------------------------------------------------------
+    for (size_t i = 0; i < ids.size(); ++i) {
+        const PcmSource &s = srcs[i];
+        drop_track(ids[i]); // HashMap::insert replaces an existing id
+        Track t;
+        t.path = s.path; t.sr = s.sr; t.ch = s.ch; t.fmt = s.fmt; t.n = s.n;
+        t.win = pre[i].win; t.hop = pre[i].hop; t.n_fft = pre[i].n_fft;
+        t.tables = tables_for(s.sr, t.win, t.n_fft);
+        const size_t esz = s.fmt == PCM_I16 ? 2 : 4;
+        if (s.on_device) t.d_pcm = s.data;
+        else {
+            const size_t bytes = s.n * s.ch * esz;
+            t.owned_pcm.alloc(bytes + 64);
+            SGX_CUDA(cudaMemcpyAsync(t.owned_pcm.p, s.data, bytes, cudaMemcpyHostToDevice, stream_));
+            t.d_pcm = t.owned_pcm.p;
+        }
+        t.n_frames = (size_t)pre[i].T;
+        t.n_out = t.tables->n_mel ? t.tables->n_mel : t.n_fft / 2 + 1;
+        t.spec.alloc(t.n_frames * t.n_out);
+        t.slot = alloc_slot();
+        const float sec = (float)t.n / (float)t.sr; // lib.rs:178-182
+        if (sec > max_sec_) { max_sec_ = sec; id_max_sec_ = ids[i]; }
+        tracks_.erase(ids[i]);
+        tracks_.emplace(ids[i], std::move(t));
+    }
+    // ---- update_specs (lib.rs:142-168): one K1 launch per FFT size -------------------------------------
+    std::map<size_t, std::vector<size_t>> by_fft;
+    for (size_t id : ids) by_fft[tracks_.at(id).n_fft].push_back(id);
+    std::vector<StftTrack> descs;
+    struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; };
+    std::vector<Group> groups;
+    for (auto &kv : by_fft) {
+        const StftConfig &cfg = ctx_->plan(kv.first).cfg;
+        int max_hop = 1;
+        for (size_t id : kv.second) max_hop = std::max<int>(max_hop, (int)tracks_.at(id).hop);
+        Group g{kv.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop), 0};
+        // a track id may appear twice in id_list; the last one wins, launch it once
+        std::vector<size_t> uniq;
+        for (size_t id : kv.second) if (std::find(uniq.begin(), uniq.end(), id) == uniq.end()) uniq.push_back(id);
+        for (size_t id : uniq) {
+            Track &t = tracks_.at(id);
+            StftTrack d = make_desc(t.d_pcm, t.fmt, t.n, t.ch, t.win, t.hop, t.n_fft, t.n_frames, *t.tables,
+                                    t.spec.p, t.n_out, slots_.p + 2 * t.slot);
+            d.tile_begin = g.n_tiles;
+            g.n_tiles += (int)((t.n_frames + g.tiling.frames_per_tile - 1) / g.tiling.frames_per_tile);
+            descs.push_back(d);
+            ++g.count;
+        }
+        groups.push_back(g);
+    }
+    d_stft_.ensure(descs.size());
+    SGX_CUDA(cudaMemcpyAsync(d_stft_.p, descs.data(), sizeof(StftTrack) * descs.size(), cudaMemcpyHostToDevice, stream_));
+    for (const Group &g : groups) {
+        FftPlan &pl = ctx_->plan(g.n_fft);
+        StftLaunch L{};
+        L.tracks = d_stft_.p + g.first; L.n_tracks = (int)g.count; L.n_tiles = g.n_tiles;
+        L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
+        L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
+        L.tile_floats = g.tiling.tile_floats; L.tw = pl.tw.p; L.split = pl.split.p;
+        SGX_CUDA(launch_stft(pl.cfg, L, stream_));
+    }
+    // ---- update_spec_greys, range part (lib.rs:193-229) ------------------------------------------------
+    reduce_and_commit(want_changed);
+    uint32_t msr = 0;
+    for (auto &kv : tracks_) msr = std::max(msr, kv.second.sr);
+    if (msr != max_sr_) { max_sr_ = msr; changed_acc_ = true; }
+    if (!want_changed) return false;
+    return synchronize();
+}
+
+bool MultiTrack::remove_track(size_t id, bool want_changed)
+{
+    SGX_CUDA(cudaSetDevice(device_));
+    auto it = tracks_.find(id);
+    if (it == tracks_.end()) throw Error(SGX_ERR_UNKNOWN_ID, "remove_track: unknown track id " + std::to_string(id));
+    drop_track(id);
+    if (id_max_sec_ == id) { // lib.rs:269-286
+        size_t best_id = 0; float best = 0.0f;
+        for (auto &kv : tracks_) {
+            const float sec = (float)kv.second.n / (float)kv.second.sr;
+            if (sec > best) { best = sec; best_id = kv.first; }
+        }
+        id_max_sec_ = best_id; max_sec_ = best;
+    }
+    reduce_and_commit(want_changed);
+    uint32_t msr = 0;
+    for (auto &kv : tracks_) msr = std::max(msr, kv.second.sr);
+    if (msr != max_sr_) { max_sr_ = msr; changed_acc_ = true; }
+    if (!want_changed) return false;
+    return synchronize();
+}
+
+const Track &MultiTrack::track(size_t id) const
+{
+    auto it = tracks_.find(id);
+    if (it == tracks_.end()) throw Error(SGX_ERR_UNKNOWN_ID, "unknown track id " + std::to_string(id));
+    return it->second;
+}
+
+float MultiTrack::frequency_hz(size_t id, float rel) const
+{
+    const float half_sr = (float)track(id).sr / 2.0f;
+    if (set_.freq_scale == SGX_FREQ_LINEAR) return half_sr * rel;
+    return mel_to_hz(hz_to_mel(half_sr) * rel);
+}
+
+uint32_t MultiTrack::image_width(size_t id, float px_per_sec) const
+{
+    const Track &t = track(id);
+    return calc_nwidth(px_per_sec, t.n, t.sr);
+}
+
+AxisTableDev *MultiTrack::axis_table(int n_in, int n_out, bool tap_major)
+{
+    const auto key = std::make_tuple(n_in, n_out, tap_major);
+    auto it = axis_.find(key);
+    if (it != axis_.end()) return it->second.get();
+    if (axis_.size() >= 128) { // bounded cache; tables may be referenced by enqueued launches
+        SGX_CUDA(cudaStreamSynchronize(stream_));
+        axis_.clear();
+    }
+    std::unique_ptr<AxisTableDev> t(new AxisTableDev());
+    t->taps = (int)lanczos3_max_taps((uint32_t)n_in, (uint32_t)n_out);
+    t->left.alloc(n_out); t->cnt.alloc(n_out); t->sum.alloc(n_out);
+    t->w.alloc((size_t)n_out * t->taps);
+    SGX_CUDA(launch_build_axis_table(n_in, n_out, t->taps, tap_major, t->left.p, t->cnt.p, t->sum.p, t->w.p, stream_));
+    AxisTableDev *raw = t.get();
+    axis_.emplace(key, std::move(t));
+    return raw;
+}
+
+void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32_t nheight, int channels,
+                        uint8_t *const *d_out, const size_t *cap, size_t *written)
+{
+    SGX_CUDA(cudaSetDevice(device_));
+    if (channels != 3 && channels != 4) throw Error(SGX_ERR_BAD_ARG, "channels must be 3 or 4");
+    if (nheight > 65535u) throw Error(SGX_ERR_BAD_ARG, "nheight too large");
+    const bool mel = set_.freq_scale == SGX_FREQ_MEL;
+    const uint32_t msr = effective_max_sr();
+    struct Item { size_t idx; int T, height, nwidth; };
+    std::vector<Item> items;
+    std::vector<RenderTrack> descs;
+    bool short_buf = false;
+    for (size_t i = 0; i < ids.size(); ++i) {
+        const Track &t = track(ids[i]);
+        const uint32_t nwidth = calc_nwidth(px_per_sec, t.n, t.sr); // lib.rs:296
+        const size_t need = (size_t)nwidth * nheight * channels;
+        if (written) written[i] = need;
+        if (need == 0) continue;
+        if (!d_out || !d_out[i]) continue; // size query
+        if (cap[i] < need) { short_buf = true; continue; }
+        const float up = calc_up_ratio(msr, t.sr, mel);            // lib.rs:231-248
+        const uint32_t height = grey_height(t.n_out, up);          // display.rs:45
+        if (height < t.n_out)
+            throw Error(SGX_ERR_STATE, "up_ratio < 1: u32 underflow at display.rs:47 (global max_sr not set?)");
+        RenderTrack r{};
+        r.src = t.spec.p; r.width = (int)t.n_frames; r.n_out = (int)t.n_out; r.height = (int)height;
+        r.nwidth = (int)nwidth; r.nheight = (int)nheight; r.out = d_out[i];
+        AxisTableDev *v = axis_table((int)height, (int)nheight, false);
+        AxisTableDev *h = axis_table((int)t.n_frames, (int)nwidth, true);
+        r.v_left = v->left.p; r.v_cnt = v->cnt.p; r.v_sum = v->sum.p; r.v_w = v->w.p; r.v_taps = v->taps;
+        r.h_left = h->left.p; r.h_cnt = h->cnt.p; r.h_sum = h->sum.p; r.h_w = h->w.p; r.h_taps = h->taps;
+        items.push_back(Item{descs.size(), r.width, r.height, r.nwidth});
+        descs.push_back(r);
+    }
+    if (!descs.empty()) {
+        // tracks with identical geometry share a launch
+        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+            return std::tie(a.T, a.height, a.nwidth) < std::tie(b.T, b.height, b.nwidth);
+        });
+        std::vector<RenderTrack> sorted;
+        for (const Item &it : items) sorted.push_back(descs[it.idx]);
+        d_render_.ensure(sorted.size());
+        SGX_CUDA(cudaMemcpyAsync(d_render_.p, sorted.data(), sizeof(RenderTrack) * sorted.size(), cudaMemcpyHostToDevice, stream_));
+        size_t a = 0;
+        while (a < items.size()) {
+            size_t b = a + 1;
+            while (b < items.size() && items[b].T == items[a].T && items[b].height == items[a].height &&
+                   items[b].nwidth == items[a].nwidth) ++b;
+            const RenderTiling tl = plan_render_tiles(items[a].T, items[a].height, items[a].nwidth, (int)nheight);
+            for (size_t c = a; c < b; c += 65535) { // gridDim.z limit
+                RenderLaunch L{};
+                L.tracks = d_render_.p + c; L.n_tracks = (int)std::min<size_t>(65535, b - c);
+                L.from_db = 1; L.range = d_state_.p; L.channels = channels;
+                L.px = tl.px; L.py = tl.py; L.fc = tl.fc; L.rv_max = tl.rv_max;
+                SGX_CUDA(launch_render(L, items[a].nwidth, (int)nheight, tl.smem_bytes, stream_));
+            }
+            a = b;
+        }
+    }
+    if (short_buf) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+}
+
+std::vector<uint8_t> MultiTrack::render_host(size_t id, float px_per_sec, uint32_t nheight, int channels)
+{
+    const Track &t = track(id);
+    const size_t need = (size_t)calc_nwidth(px_per_sec, t.n, t.sr) * nheight * channels;
+    std::vector<uint8_t> host(need);
+    if (need == 0) return host;
+    DevBuf<uint8_t> d;
+    d.alloc(need);
+    uint8_t *outs[1] = {d.p};
+    size_t caps[1] = {need}, wr[1] = {0};
+    render({id}, px_per_sec, nheight, channels, outs, caps, wr);
+    SGX_CUDA(cudaMemcpyAsync(host.data(), d.p, need, cudaMemcpyDeviceToHost, stream_));
+    SGX_CUDA(cudaStreamSynchronize(stream_));
+    return host;
+}
+
+std::vector<uint8_t> MultiTrack::wav_image(size_t id, float px_per_sec, uint32_t nheight, float amp_min, float amp_max)
+{
+    SGX_CUDA(cudaSetDevice(device_));
+    const Track &t = track(id);
+    const uint32_t nwidth = calc_nwidth(px_per_sec, t.n, t.sr); // lib.rs:308
+    const size_t need = (size_t)nwidth * nheight * 4;
+    std::vector<uint8_t> host(need);
+    if (need == 0) return host;
+    DevBuf<uint8_t> d; d.alloc(need);
+    DevBuf<int> flag; flag.alloc(1);
+    SGX_CUDA(cudaMemsetAsync(d.p, 0, need, stream_));
+    SGX_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), stream_));
+    SGX_CUDA(launch_wav_image(t.d_pcm, t.fmt, (int)t.ch, (long long)t.n, (int)nwidth, (int)nheight, amp_min, amp_max, d.p, flag.p, stream_));
+    int bad = 0;
+    SGX_CUDA(cudaMemcpyAsync(host.data(), d.p, need, cudaMemcpyDeviceToHost, stream_));
+    SGX_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    SGX_CUDA(cudaStreamSynchronize(stream_));
+    if (bad) throw Error(SGX_ERR_BAD_ARG, "wav_to_image: empty sample slice for a pixel column (the reference panics, display.rs:95)");
+    return host;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage functions (surface 2): host in, host out, current device, default stream
+// ---------------------------------------------------------------------------------------------------
+static int current_device()
+{
+    int d = 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) { cudaGetLastError(); throw Error(SGX_ERR_CUDA, "no usable CUDA device (this engine has no CPU path)"); }
+    return d;
+}
+
+StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t hop, size_t n_fft,
+                    const float *window, const float *mel_fb, size_t n_mel, float *out, size_t cap_elems)
+{
+    DeviceCtx &ctx = DeviceCtx::get(current_device());
+    long T = 0;
+    check_stft_args(n, win, hop, n_fft, &T);
+    if (mode == MODE_MEL_DB && (!mel_fb || n_mel == 0)) throw Error(SGX_ERR_BAD_ARG, "mel filterbank missing (mel.rs:51 assert_ne!(n_mel, 0))");
+    const size_t B = n_fft / 2 + 1;
+    const size_t n_out = mode == MODE_MEL_DB ? n_mel : B;
+    const size_t elems = (size_t)T * n_out * (mode == MODE_COMPLEX ? 2 : 1);
+    StageOut so{(size_t)T, n_out};
+    if (!out) return so;
+    if (cap_elems < elems) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+    cudaStream_t s = 0;
+    FftPlan &pl = ctx.plan(n_fft);
+    std::vector<float> wbuf;
+    if (!window) { wbuf.resize(win); calc_window(win, n_fft, wbuf.data()); window = wbuf.data(); } // lib.rs:403-408
+    TrackTables tt;
+    fill_tables(tt, win, n_fft, window, mode == MODE_MEL_DB ? mel_fb : nullptr, n_mel, pl.cfg, s);
+    DevBuf<float> d_in, d_out;
+    d_in.alloc(n + 16); d_out.alloc(elems);
+    SGX_CUDA(cudaMemcpyAsync(d_in.p, input, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    StftTrack d = make_desc(d_in.p, PCM_F32, n, 1, win, hop, n_fft, (size_t)T, tt, d_out.p, n_out, nullptr);
+    const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop);
+    DevBuf<StftTrack> dd; dd.upload(&d, 1, s);
+    StftLaunch L{};
+    L.tracks = dd.p; L.n_tracks = 1;
+    L.n_tiles = (int)(((size_t)T + tl.frames_per_tile - 1) / tl.frames_per_tile);
+    L.mode = mode; L.frames_per_tile = tl.frames_per_tile; L.staged = tl.staged; L.tile_floats = tl.tile_floats;
+    L.tw = pl.tw.p; L.split = pl.split.p;
+    SGX_CUDA(launch_stft(pl.cfg, L, s));
+    SGX_CUDA(cudaMemcpyAsync(out, d_out.p, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SGX_CUDA(cudaStreamSynchronize(s));
+    return so;
+}
+
+void stage_amp_to_db(float *x, size_t n)
+{
+    DeviceCtx::get(current_device());
+    if (n == 0) return;
+    DevBuf<float> d; d.alloc(n);
+    DevBuf<int> flag; flag.alloc(1);
+    SGX_CUDA(cudaMemcpyAsync(d.p, x, n * sizeof(float), cudaMemcpyHostToDevice, 0));
+    SGX_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), 0));
+    SGX_CUDA(launch_amp_to_db(d.p, n, flag.p, 0));
+    int bad = 0;
+    SGX_CUDA(cudaMemcpy(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) throw Error(SGX_ERR_BAD_ARG, "amp_to_db: negative or NaN input (assert at decibel.rs:34)");
+    SGX_CUDA(cudaMemcpy(x, d.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+uint32_t stage_spec_to_grey(const float *spec, size_t T, size_t n_out, float up_ratio, float max_db,
+                            float min_db, float *grey, size_t cap)
+{
+    DeviceCtx::get(current_device());
+    const uint32_t height = grey_height(n_out, up_ratio);
+    if (!grey) return height;
+    if (height < n_out) throw Error(SGX_ERR_BAD_ARG, "up_ratio < 1: u32 underflow at display.rs:47");
+    const size_t elems = (size_t)T * height;
+    if (cap < elems) throw Error(SGX_ERR_BUFFER, "grey buffer too small");
+    if (elems == 0) return height;
+    DevBuf<float> ds, dg; ds.alloc(T * n_out); dg.alloc(elems);
+    SGX_CUDA(cudaMemcpyAsync(ds.p, spec, T * n_out * sizeof(float), cudaMemcpyHostToDevice, 0));
+    SGX_CUDA(launch_spec_to_grey(ds.p, (int)T, (int)n_out, (int)height, max_db, min_db, dg.p, 0));
+    SGX_CUDA(cudaMemcpy(grey, dg.p, elems * sizeof(float), cudaMemcpyDeviceToHost));
+    return height;
+}
+
+void stage_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint32_t nwidth, uint32_t nheight,
+                       int channels, uint8_t *out, size_t cap)
+{
+    DeviceCtx::get(current_device());
+    if (channels != 3 && channels != 4) throw Error(SGX_ERR_BAD_ARG, "channels must be 3 or 4");
+    if (!width || !height || !nwidth || !nheight) throw Error(SGX_ERR_BAD_ARG, "empty image");
+    const size_t need = (size_t)nwidth * nheight * channels;
+    if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+    cudaStream_t s = 0;
+    DevBuf<float> dg; dg.alloc((size_t)width * height);
+    DevBuf<uint8_t> dout; dout.alloc(need);
+    SGX_CUDA(cudaMemcpyAsync(dg.p, grey, (size_t)width * height * sizeof(float), cudaMemcpyHostToDevice, s));
+    AxisTableDev v, h;
+    v.taps = (int)lanczos3_max_taps(height, nheight); h.taps = (int)lanczos3_max_taps(width, nwidth);
+    v.left.alloc(nheight); v.cnt.alloc(nheight); v.sum.alloc(nheight); v.w.alloc((size_t)nheight * v.taps);
+    h.left.alloc(nwidth); h.cnt.alloc(nwidth); h.sum.alloc(nwidth); h.w.alloc((size_t)nwidth * h.taps);
+    SGX_CUDA(launch_build_axis_table((int)height, (int)nheight, v.taps, false, v.left.p, v.cnt.p, v.sum.p, v.w.p, s));
+    SGX_CUDA(launch_build_axis_table((int)width, (int)nwidth, h.taps, true, h.left.p, h.cnt.p, h.sum.p, h.w.p, s));
+    RenderTrack r{};
+    r.src = dg.p; r.width = (int)width; r.n_out = (int)height; r.height = (int)height;
+    r.nwidth = (int)nwidth; r.nheight = (int)nheight; r.out = dout.p;
+    r.v_left = v.left.p; r.v_cnt = v.cnt.p; r.v_sum = v.sum.p; r.v_w = v.w.p; r.v_taps = v.taps;
+    r.h_left = h.left.p; r.h_cnt = h.cnt.p; r.h_sum = h.sum.p; r.h_w = h.w.p; r.h_taps = h.taps;
+    DevBuf<RenderTrack> dr; dr.upload(&r, 1, s);
+    const RenderTiling tl = plan_render_tiles((int)width, (int)height, (int)nwidth, (int)nheight);
+    RenderLaunch L{};
+    L.tracks = dr.p; L.n_tracks = 1; L.from_db = 0; L.range = nullptr; L.channels = channels;
+    L.px = tl.px; L.py = tl.py; L.fc = tl.fc; L.rv_max = tl.rv_max;
+    SGX_CUDA(launch_render(L, (int)nwidth, (int)nheight, tl.smem_bytes, s));
+    SGX_CUDA(cudaMemcpyAsync(out, dout.p, need, cudaMemcpyDeviceToHost, s));
+    SGX_CUDA(cudaStreamSynchronize(s));
+}
+
+void stage_wav_to_image(const float *wav, size_t n, uint32_t nwidth, uint32_t nheight, float amp_min,
+                        float amp_max, uint8_t *out, size_t cap)
+{
+    DeviceCtx::get(current_device());
+    const size_t need = (size_t)nwidth * nheight * 4;
+    if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+    if (need == 0) return;
+    if (n == 0) throw Error(SGX_ERR_BAD_ARG, "empty waveform");
+    DevBuf<float> dw; dw.alloc(n);
+    DevBuf<uint8_t> d; d.alloc(need);
+    DevBuf<int> flag; flag.alloc(1);
+    SGX_CUDA(cudaMemcpyAsync(dw.p, wav, n * sizeof(float), cudaMemcpyHostToDevice, 0));
+    SGX_CUDA(cudaMemsetAsync(d.p, 0, need, 0));
+    SGX_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), 0));
+    SGX_CUDA(launch_wav_image(dw.p, PCM_F32, 1, (long long)n, (int)nwidth, (int)nheight, amp_min, amp_max, d.p, flag.p, 0));
+    int bad = 0;
+    SGX_CUDA(cudaMemcpy(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) throw Error(SGX_ERR_BAD_ARG, "wav_to_image: empty sample slice for a pixel column (the reference panics, display.rs:95)");
+    SGX_CUDA(cudaMemcpy(out, d.p, need, cudaMemcpyDeviceToHost));
+}
+
+} // namespace sgx

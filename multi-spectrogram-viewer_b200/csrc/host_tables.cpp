@@ -1,0 +1,204 @@
+// host_tables.cpp -- see host_tables.h.  All arithmetic is f32 in the reference's operation
+// order (build with -ffp-contract=off); tests/test_host_tables.py checks every function
+// bit-for-bit against the CPU oracle.
+#include "host_tables.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace sgx {
+
+static const double kPi = 3.14159265358979323846264338327950288;
+
+size_t calc_proper_n_fft(size_t win_length)
+{
+    // utils.rs:18: 2usize.pow((win_length as f32).log2().ceil() as u32)
+    float e = std::ceil(std::log2((float)win_length));
+    if (!(e > 0.0f)) return 1;
+    return (size_t)1 << (unsigned)e;
+}
+
+void hann(size_t size, bool symmetric, float *out)
+{
+    // windows.rs:7-19 with (a,b,c,d) = (0.5,0.5,0,0): x = pi*i/(size2-1);
+    // (a - b*cos(2x)) + (c*cos(4x) - d*cos(6x))
+    const float pi = (float)kPi;
+    const size_t size2 = symmetric ? size : size + 1;
+    const float denom = (float)(size2 - 1);
+    for (size_t i = 0; i < size; ++i) {
+        float x = pi * (float)i / denom;
+        float t1 = 0.5f * std::cos(2.0f * x);
+        float t2 = 0.0f * std::cos(4.0f * x);
+        float t3 = 0.0f * std::cos(6.0f * x);
+        out[i] = (0.5f - t1) + (t2 - t3);
+    }
+}
+
+void calc_window(size_t win_length, size_t n_fft, float *out)
+{
+    hann(win_length, false, out);
+    const float d = (float)n_fft;
+    for (size_t i = 0; i < win_length; ++i) out[i] = out[i] / d;
+}
+
+// mel.rs:8-11
+static const float kMinLogMel = 15.0f;
+static const float kMinLogHz = (float)1000.0;
+static const float kLogStep = (float)0.06875177742094912;
+static const float kLinearScale = (float)(200.0 / 3.0);
+
+float mel_to_hz(float mel)
+{
+    if (mel < kMinLogMel) return kLinearScale * mel;
+    return kMinLogHz * std::exp(kLogStep * (mel - kMinLogMel));
+}
+
+float hz_to_mel(float hz)
+{
+    if (hz < kMinLogHz) return hz / kLinearScale;
+    return kMinLogMel + std::log(hz / kMinLogHz) / kLogStep;
+}
+
+// ndarray Array::linspace(a,b,n): a + i*((b-a)/(n-1))
+static void linspace(float a, float b, size_t n, std::vector<float> &v)
+{
+    v.resize(n);
+    const float step = n > 1 ? (b - a) / (float)(n - 1) : 0.0f;
+    for (size_t i = 0; i < n; ++i) v[i] = a + step * (float)i;
+}
+
+void calc_mel_fb(uint32_t sr, size_t n_fft, size_t n_mel, float fmin, float fmax, bool do_norm,
+                 float *out)
+{
+    const float nyq = (float)sr / 2.0f;
+    if (fmax < 0.0f) fmax = nyq;
+    const size_t n_freq = n_fft / 2 + 1;
+    std::vector<float> lin, edges;
+    linspace(0.0f, nyq, n_freq, lin);
+    linspace(hz_to_mel(fmin), hz_to_mel(fmax), n_mel + 2, edges);
+    for (float &e : edges) e = mel_to_hz(e);
+    std::memset(out, 0, sizeof(float) * n_freq * n_mel);
+    for (size_t m = 0; m < n_mel; ++m) {
+        const float f0 = edges[m], f1 = edges[m + 1], f2 = edges[m + 2];
+        for (size_t b = 0; b < n_freq; ++b) { // mel.rs:67-79
+            const float f = lin[b];
+            if (f <= f0) continue;
+            if (f0 < f && f < f1) out[b * n_mel + m] = (f - f0) / (f1 - f0);
+            else if (f == f1) out[b * n_mel + m] = 1.0f;
+            else if (f1 < f && f < f2) out[b * n_mel + m] = (f2 - f) / (f2 - f1);
+            else break;
+        }
+        if (do_norm) { // mel.rs:80-82
+            float s = 0.0f;
+            for (size_t b = 0; b < n_freq; ++b) s += out[b * n_mel + m];
+            const float eps = 1.1920929e-07f;
+            const float d = s > eps ? s : eps;
+            for (size_t b = 0; b < n_freq; ++b) out[b * n_mel + m] = out[b * n_mel + m] / d;
+        }
+    }
+}
+
+size_t calc_mel_fb_default(uint32_t sr, size_t n_fft, std::vector<float> &fb)
+{
+    const size_t n_freq = n_fft / 2 + 1;
+    const float guess =
+        2.0f * hz_to_mel((float)sr / 2.0f) / hz_to_mel((float)sr / (float)n_fft) - 1.0f;
+    size_t n_mel = guess > 0.0f ? (size_t)guess : 0; // `as usize`: truncating, saturating
+    n_mel = std::min(n_mel, n_freq);
+    for (;;) {
+        fb.assign(n_freq * std::max<size_t>(n_mel, 1), 0.0f);
+        if (n_mel == 0) break; // the reference would assert (mel.rs:51); callers treat 0 as error
+        calc_mel_fb(sr, n_fft, n_mel, 0.0f, -1.0f, true, fb.data());
+        bool all_pos = true;
+        for (size_t m = 0; m < n_mel && all_pos; ++m) {
+            float s = 0.0f;
+            for (size_t b = 0; b < n_freq; ++b) s += fb[b * n_mel + m];
+            all_pos = s > 0.0f;
+        }
+        if (all_pos) break;
+        --n_mel;
+    }
+    fb.resize(n_freq * n_mel);
+    return n_mel;
+}
+
+static size_t count_windows(size_t len, size_t w, size_t hop)
+{
+    return len < w ? 0 : (len - w) / hop + 1; // ndarray .windows(w).step_by(hop)
+}
+
+long stft_num_frames(size_t n, size_t win, size_t hop)
+{
+    if (win < 2 || hop < 1 || n < win) return -1;
+    const size_t half = win / 2;
+    if (half + 1 > n || half + 1 > win - 1) return -1; // reflect pads need x[1..=half]
+    // lib.rs:412-418  front: input[..win-1] left-padded by half
+    const size_t n_front = count_windows(win - 1 + half, win, hop);
+    if (n_front * hop < half) return -1; // usize underflow at lib.rs:420
+    size_t first = n_front * hop - half;
+    if (first > n) return -1;
+    // lib.rs:420-421  middle
+    const size_t n_mid = count_windows(n - first, win, hop);
+    first += n_mid * hop;
+    // lib.rs:423-433  back
+    const size_t back_start = std::min(first, n - half - 1);
+    const size_t back_len = (n - back_start) + half - (first - back_start);
+    const size_t n_back = count_windows(back_len, win, hop);
+    return (long)(n_front + n_mid + n_back);
+}
+
+uint32_t calc_nwidth(float px_per_sec, size_t n, uint32_t sr)
+{
+    const float v = px_per_sec * (float)n / (float)sr;
+    if (!(v > 0.0f)) return 0;
+    if (v >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)v;
+}
+
+float calc_up_ratio(uint32_t max_sr, uint32_t sr, bool mel)
+{
+    if (!mel) return (float)max_sr / (float)sr;
+    return hz_to_mel((float)max_sr / 2.0f) / hz_to_mel((float)sr / 2.0f);
+}
+
+uint32_t grey_height(size_t n_out, float up_ratio)
+{
+    return (uint32_t)std::round((float)n_out * up_ratio);
+}
+
+MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group)
+{
+    MelBands mb;
+    mb.lo.resize(n_mel); mb.cnt.resize(n_mel); mb.off.resize(n_mel);
+    for (size_t m = 0; m < n_mel; ++m) {
+        long lo = -1, hi = -1;
+        for (size_t b = 0; b < n_freq; ++b)
+            if (fb[b * n_mel + m] != 0.0f) { if (lo < 0) lo = (long)b; hi = (long)b; }
+        mb.off[m] = (int)mb.w.size();
+        if (lo < 0) { mb.lo[m] = 0; mb.cnt[m] = 0; continue; }
+        mb.lo[m] = (int)lo;
+        mb.cnt[m] = (int)(hi - lo + 1);
+        mb.max_cnt = std::max(mb.max_cnt, mb.cnt[m]);
+        for (long b = lo; b <= hi; ++b) mb.w.push_back(fb[(size_t)b * n_mel + m]);
+    }
+    if (mb.w.empty()) mb.w.push_back(0.0f);
+    // lanes per filter: minimise   sum over rounds of (longest band in the round / P)  + shuffles
+    int best = 0; double best_cost = 1e300;
+    for (int lg = 0; lg <= 5; ++lg) {
+        const int P = 1 << lg;
+        const size_t per_round = (size_t)std::max(1, threads_per_group / P);
+        double cost = 0.0;
+        for (size_t m0 = 0; m0 < n_mel; m0 += per_round) {
+            int longest = 0;
+            for (size_t m = m0; m < std::min(n_mel, m0 + per_round); ++m)
+                longest = std::max(longest, mb.cnt[m]);
+            cost += 2.0 * std::ceil((double)longest / P) + 1.5 * lg + 3.0;
+        }
+        if (cost < best_cost) { best_cost = cost; best = lg; }
+    }
+    mb.log2_split = best;
+    return mb;
+}
+
+} // namespace sgx

@@ -1,0 +1,66 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (implemented in *.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_common.cuh"
+
+namespace sgx {
+
+// Static configuration of the fused analysis kernel K1 for one FFT size.
+struct StftConfig {
+    int n_fft;             // F
+    int h;                 // F/2 complex points
+    int pts;               // points per thread (radix of the main passes)
+    int vec;               // frames processed together by one thread group (V)
+    int groups;            // thread groups per CTA (G)
+    int threads;           // G * h / pts
+    size_t fft_smem;       // bytes of FFT exchange buffers
+    bool generic;          // small-F fallback kernel (one CTA per frame)
+};
+bool stft_config_for(size_t n_fft, StftConfig *cfg);
+size_t stft_max_dynamic_smem();
+
+// Enqueues K1.  `launch` carries device pointers; tile geometry must come from plan_stft_tiles.
+cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &launch, cudaStream_t stream);
+
+// Chooses frames per tile / staging for a set of (hop) values sharing one FFT size.
+struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; };
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop);
+
+// FFT twiddle tables for one size (host vectors -> caller uploads).
+void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);
+
+// K2: global dB range (lib.rs:193-209)
+cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s);
+// reduces slots [n][2] -> local {max, -min}
+cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *local_max_negmin,
+                                cudaStream_t s);
+// {max, -min} -> state {max_db, min_db, changed}: the clamps of lib.rs:208-209 and the sticky
+// 1e-3 change detection of lib.rs:210-218, all on the device
+cudaError_t launch_range_commit(const float *max_negmin, float db_range, float *state,
+                                cudaStream_t s);
+
+// K3: render
+struct AxisTable { int *left, *cnt; float *sum, *w; int taps; int n_in, n_out; bool tap_major; };
+uint32_t lanczos3_max_taps(uint32_t n_in, uint32_t n_out);
+cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_major, int *left,
+                                    int *cnt, float *sum, float *w, cudaStream_t s);
+struct RenderTiling { int px, py, fc, rv_max; size_t smem_bytes; };
+RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight);
+cudaError_t launch_render(const RenderLaunch &launch, int max_nwidth, int max_nheight,
+                          size_t smem_bytes, cudaStream_t s);
+
+// small elementwise kernels of the stage API
+cudaError_t launch_spec_to_grey(const float *spec, int n_frames, int n_out, int height, float max_db,
+                                float min_db, float *grey, cudaStream_t s);
+cudaError_t launch_amp_to_db(float *x, size_t n, int *bad_flag, cudaStream_t s);
+cudaError_t launch_wav_image(const void *pcm, int fmt, int ch, long long n, int nwidth, int nheight,
+                             float amp_min, float amp_max, unsigned char *out, int *err_flag,
+                             cudaStream_t s);
+
+void count_launch(int n = 1);
+uint64_t launch_count();
+
+} // namespace sgx

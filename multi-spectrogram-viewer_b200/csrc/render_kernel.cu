@@ -1,0 +1,451 @@
+// render_kernel.cu -- K2 (global dB range) and K3 (fused rasteriser), sm_100a.
+//
+// K3 turns the cached dB spectrogram of a batch of tracks into pixels in one pass:
+//   normalise / clip / vertical flip / top padding    display.rs:44-54  (spec_to_grey)
+//   separable Lanczos3 resample, vertical then horizontal, each pass followed by the clamp to
+//   [0, f32::MAX] of image 0.23's imageops::resize                     display.rs:57
+//   10-stop colour map                                                  display.rs:24-42
+//   RGB / RGBA bytes, row 0 = highest frequency                         display.rs:56-61
+// The grey image and the vertically resampled intermediate only ever exist as shared-memory
+// tiles; HBM sees one read of dB and one write of pixels.
+#include <cstdint>
+
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace sgx {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// K2
+// ---------------------------------------------------------------------------------------------------
+__global__ void range_init_kernel(unsigned *slots, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        slots[2 * i] = enc_ordered(-INFINITY);    // lib.rs:203 identity of the reduce
+        slots[2 * i + 1] = enc_ordered(INFINITY);
+    }
+}
+
+__global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, float *out)
+{
+    __shared__ float smax[32], smin[32];
+    float mx = -INFINITY, mn = INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        mx = fmaxf(mx, dec_ordered(slots[2 * i]));
+        mn = fminf(mn, dec_ordered(slots[2 * i + 1]));
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+    }
+    if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = mx; smin[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)blockDim.x / 32; ++w) { mx = fmaxf(mx, smax[w]); mn = fminf(mn, smin[w]); }
+        out[0] = mx;  // all-reduce(MAX) friendly pair {max, -min}
+        out[1] = -mn;
+    }
+}
+
+// approx::abs_diff_ne!(a, b, epsilon = e): !( |a-b| <= e ), with the subtraction ordered as approx does
+__device__ __forceinline__ bool abs_diff_ne(float a, float b, float eps)
+{
+    const float d = a > b ? a - b : b - a;
+    return !(d <= eps);
+}
+
+__global__ void range_commit_kernel(const float *__restrict__ max_negmin, float db_range, float *state)
+{
+    // lib.rs:208-209: max = max.min(0.); min = min.max(max - db_range)
+    const float mx = fminf(max_negmin[0], 0.0f);
+    const float mn = fmaxf(-max_negmin[1], mx - db_range);
+    // lib.rs:210-218: the stored range only moves when it differs by more than 1e-3
+    if (abs_diff_ne(state[0], mx, 1e-3f)) { state[0] = mx; state[2] = 1.0f; }
+    if (abs_diff_ne(state[1], mn, 1e-3f)) { state[1] = mn; state[2] = 1.0f; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lanczos3 tap tables (image 0.23 horizontal_sample / vertical_sample geometry).  One thread per
+// output index; every f32 operation is a separately rounded IEEE op (no FMA contraction) so the
+// tap windows are exactly the ones the CPU code derives.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sinc_dev(float t)
+{
+    const float a = __fmul_rn(t, 3.14159265358979323846f);
+    return t == 0.0f ? 1.0f : __fdiv_rn(sinf(a), a);
+}
+__device__ __forceinline__ float lanczos3_dev(float x)
+{
+    return fabsf(x) < 3.0f ? __fmul_rn(sinc_dev(x), sinc_dev(__fdiv_rn(x, 3.0f))) : 0.0f;
+}
+
+__global__ void build_axis_table_kernel(int n_in, int n_out, int taps, int tap_major, int *left_o,
+                                        int *cnt_o, float *sum_o, float *w_o)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    const float ratio = __fdiv_rn((float)n_in, (float)n_out);
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    const float support = __fmul_rn(3.0f, sratio);
+    float inputx = __fmul_rn(__fadd_rn((float)o, 0.5f), ratio);
+    long long l = (long long)floorf(__fsub_rn(inputx, support));
+    l = l < 0 ? 0 : (l > (long long)n_in - 1 ? (long long)n_in - 1 : l);
+    long long r = (long long)ceilf(__fadd_rn(inputx, support));
+    r = r < l + 1 ? l + 1 : (r > (long long)n_in ? (long long)n_in : r);
+    inputx = __fsub_rn(inputx, 0.5f);
+    int cnt = (int)(r - l);
+    if (cnt > taps) cnt = taps; // cannot happen when taps == lanczos3_max_taps(n_in, n_out)
+    float sum = 0.0f;
+    for (int i = 0; i < taps; ++i) {
+        float w = 0.0f;
+        if (i < cnt) {
+            w = lanczos3_dev(__fdiv_rn(__fsub_rn((float)(l + i), inputx), sratio));
+            sum = __fadd_rn(sum, w);
+        }
+        if (tap_major) w_o[(size_t)i * n_out + o] = w; else w_o[(size_t)o * taps + i] = w;
+    }
+    left_o[o] = (int)l; cnt_o[o] = cnt; sum_o[o] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------------------------------
+__constant__ unsigned char kColormap[10][3] = { // display.rs:10-21
+    {0, 0, 4},     {27, 12, 65},  {74, 12, 107}, {120, 28, 109}, {165, 44, 96},
+    {207, 68, 70}, {237, 105, 37}, {251, 155, 6}, {247, 209, 61}, {252, 255, 164}};
+
+__device__ __forceinline__ float clamp_pos(float v)
+{
+    // image's clamp(v, 0, f32::MAX): `if a < min {min} else if a > max {max} else {a}`
+    return v < 0.0f ? 0.0f : (v > 3.4028235e38f ? 3.4028235e38f : v);
+}
+
+// display.rs:24-42 convert_grey_to_color; cm = colour map as floats in shared memory
+__device__ __forceinline__ uchar4 grey_to_color(float x, const float *cm)
+{
+    const float position = __fmul_rn(10.0f, x);
+    const float fl = floorf(position);
+    if (!(fl < 9.0f)) return make_uchar4(252, 255, 164, 255); // index >= len-1 (also +inf)
+    const int idx = (int)fl;
+    const float ratio = __fsub_rn(position, fl);
+    const float om = __fsub_rn(1.0f, ratio);
+    unsigned char c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float a = cm[idx * 3 + k], b = cm[idx * 3 + 3 + k];
+        const float v = roundf(__fadd_rn(__fmul_rn(ratio, b), __fmul_rn(om, a))); // half away from 0
+        c[k] = (unsigned char)fminf(fmaxf(v, 0.0f), 255.0f);
+    }
+    return make_uchar4(c[0], c[1], c[2], 255);
+}
+
+constexpr int kRenderThreads = 256;
+constexpr int kMaxPpt = 16; // output pixels per thread
+
+__global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaunch L)
+{
+    extern __shared__ __align__(16) float rsm[];
+    __shared__ float cm[30];
+    const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
+    const int nwidth = tr->nwidth, nheight = tr->nheight;
+    const int ox0 = blockIdx.x * L.px, oy0 = blockIdx.y * L.py;
+    if (ox0 >= nwidth || oy0 >= nheight) return;
+    const int pxc = min(L.px, nwidth - ox0), pyc = min(L.py, nheight - oy0);
+    const int tid = threadIdx.x;
+    if (tid < 30) cm[tid] = (float)kColormap[tid / 3][tid % 3];
+
+    const int *__restrict__ h_left = tr->h_left; const int *__restrict__ h_cnt = tr->h_cnt;
+    const int *__restrict__ v_left = tr->v_left; const int *__restrict__ v_cnt = tr->v_cnt;
+    const float *__restrict__ v_w = tr->v_w; const float *__restrict__ h_w = tr->h_w;
+    const int v_taps = tr->v_taps;
+    const float *__restrict__ src = tr->src;
+    const int width = tr->width, height = tr->height, n_out = tr->n_out;
+
+    // source window of this tile
+    const int fl = h_left[ox0];
+    const int fr = h_left[ox0 + pxc - 1] + h_cnt[ox0 + pxc - 1];
+    const int yl = v_left[oy0];
+    const int yr = v_left[oy0 + pyc - 1] + v_cnt[oy0 + pyc - 1];
+    const int rv = yr - yl;                  // grey rows needed (<= L.rv_max)
+    const int gp = L.rv_max | 1;             // odd pitch of the grey tile   [frame][row]
+    const int tp = L.fc + 1;                 // pitch of the vertical result [row][frame]
+    float *gs = rsm;
+    float *ts = rsm + (size_t)L.fc * gp;
+
+    float max_db = 0.0f, inv_span = 0.0f, min_db = 0.0f;
+    if (L.from_db) { max_db = L.range[0]; min_db = L.range[1]; inv_span = max_db - min_db; }
+    const int pad_rows = height - n_out; // grey rows above the spectrogram are 0 (display.rs:47-52)
+
+    float acc[kMaxPpt];
+#pragma unroll
+    for (int i = 0; i < kMaxPpt; ++i) acc[i] = 0.0f;
+
+    for (int c0 = fl; c0 < fr; c0 += L.fc) {
+        const int nf = min(L.fc, fr - c0);
+        __syncthreads(); // previous chunk fully consumed
+        // ---- grey tile: gs[fx][y - yl] ---------------------------------------------------------------
+        for (int e = tid; e < nf * rv; e += kRenderThreads) {
+            const int fx = e / rv, yy = e - fx * rv;
+            const int y = yl + yy;
+            float g;
+            if (L.from_db) {
+                if (y >= pad_rows) {
+                    const float db = __ldg(src + (size_t)(c0 + fx) * n_out + (height - 1 - y));
+                    g = fminf(fmaxf(__fdiv_rn(__fsub_rn(db, min_db), inv_span), 0.0f), 1.0f);
+                } else g = 0.0f;
+            } else {
+                g = __ldg(src + (size_t)y * width + (c0 + fx));
+            }
+            gs[fx * gp + yy] = g;
+        }
+        __syncthreads();
+        // ---- vertical pass: ts[oy][fx] ------------------------------------------------------------------
+        for (int e = tid; e < pyc * nf; e += kRenderThreads) {
+            const int oyl = e / nf, fx = e - oyl * nf;
+            const int oy = oy0 + oyl;
+            const int l = v_left[oy] - yl, cnt = v_cnt[oy];
+            const float *wrow = v_w + (size_t)oy * v_taps;
+            const float *g = gs + fx * gp + l;
+            float t = 0.0f;
+            for (int i = 0; i < cnt; ++i) t = fmaf(g[i], __ldg(wrow + i), t);
+            ts[oyl * tp + fx] = clamp_pos(__fdiv_rn(t, tr->v_sum[oy]));
+        }
+        __syncthreads();
+        // ---- horizontal pass, accumulated per pixel across chunks ----------------------------------------
+#pragma unroll
+        for (int q = 0; q < kMaxPpt; ++q) {
+            const int p = tid + q * kRenderThreads;
+            if (p < pxc * pyc) {
+                const int oyl = p / pxc, oxl = p - oyl * pxc;
+                const int ox = ox0 + oxl;
+                const int l = h_left[ox], cnt = h_cnt[ox];
+                const int i0 = max(l, c0), i1 = min(l + cnt, c0 + nf);
+                float t = acc[q];
+                for (int i = i0; i < i1; ++i)
+                    t = fmaf(ts[oyl * tp + (i - c0)], __ldg(h_w + (size_t)(i - l) * nwidth + ox), t);
+                acc[q] = t;
+            }
+        }
+    }
+    // ---- clamp, colour, store ------------------------------------------------------------------------------
+    unsigned char *__restrict__ outp = tr->out;
+#pragma unroll
+    for (int q = 0; q < kMaxPpt; ++q) {
+        const int p = tid + q * kRenderThreads;
+        if (p < pxc * pyc) {
+            const int oyl = p / pxc, oxl = p - oyl * pxc;
+            const int ox = ox0 + oxl, oy = oy0 + oyl;
+            const float g = clamp_pos(__fdiv_rn(acc[q], tr->h_sum[ox]));
+            const uchar4 c = grey_to_color(g, cm);
+            const size_t pix = (size_t)oy * nwidth + ox;
+            if (L.channels == 4) reinterpret_cast<uchar4 *>(outp)[pix] = c;
+            else { outp[pix * 3] = c.x; outp[pix * 3 + 1] = c.y; outp[pix * 3 + 2] = c.z; }
+        }
+    }
+}
+
+// display.rs:44-54 as a stand-alone stage (surface 2)
+__global__ void spec_to_grey_kernel(const float *__restrict__ spec, int T, int n_out, int height,
+                                    float max_db, float min_db, float *__restrict__ grey)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)T * height) return;
+    const int y = (int)(i / T), x = (int)(i - (size_t)y * T);
+    float g = 0.0f;
+    if (y >= height - n_out) {
+        const float db = spec[(size_t)x * n_out + (height - 1 - y)];
+        g = fminf(fmaxf(__fdiv_rn(__fsub_rn(db, min_db), __fsub_rn(max_db, min_db)), 0.0f), 1.0f);
+    }
+    grey[i] = g;
+}
+
+// decibel.rs:33-88 as a stand-alone stage
+__global__ void amp_to_db_kernel(float *x, size_t n, int *bad)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    if (!(v >= 0.0f)) { atomicExch(bad, 1); return; } // decibel.rs:34 assert
+    x[i] = v > 1e-18f ? __fmul_rn(20.0f, log10f(v)) : -360.0f;
+}
+
+// display.rs:63-115 wav_to_image: one thread per pixel column
+__global__ void wav_image_kernel(const void *pcm, int fmt, int ch, long long n_in, int nwidth,
+                                 int nheight, float amp_min, float amp_max,
+                                 unsigned char *__restrict__ out, int *err)
+{
+    const int i_px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i_px >= nwidth) return;
+    const PcmFormat f = (PcmFormat)fmt;
+    auto sample = [&](long long i) -> float {
+        float s = 0.0f;
+        if (f == PCM_F32) { const float *p = (const float *)pcm + i * ch; for (int c = 0; c < ch; ++c) s += p[c]; }
+        else { const short *p = (const short *)pcm + i * ch; for (int c = 0; c < ch; ++c) s += (float)p[c] * (1.0f / 32768.0f); }
+        return s;
+    };
+    const float spp = __fdiv_rn((float)n_in, (float)nwidth); // samples_per_px, display.rs:75
+    long long n = n_in;
+    long long factor = 1;
+    const bool up = spp < 1.0f;
+    if (up) { factor = (long long)ceilf(__fdiv_rn(1.0f, spp)); n = factor * n_in; }
+    auto wav_at = [&](long long i) -> float {
+        if (!up) return sample(i);
+        // display.rs:78-87 linear interpolation by `factor`
+        const long long i0 = i / factor;
+        const float b = (i0 + 1 < n_in) ? sample(i0 + 1) : 0.0f;
+        const float fr = __fdiv_rn((float)(i % factor), (float)factor);
+        return __fadd_rn(__fmul_rn(b, fr), __fmul_rn(sample(i0), __fsub_rn(1.0f, fr)));
+    };
+    const float fs = fmaxf(roundf(__fmul_rn(__fsub_rn((float)i_px, 1.5f), spp)), 0.0f);
+    const long long i_start = (long long)fs;
+    const float fe = roundf(__fmul_rn(__fadd_rn((float)i_px, 1.5f), spp));
+    long long i_end = fe <= 0.0f ? 0 : (long long)fe;
+    if (i_end > n) i_end = n;
+    if (i_start >= i_end) { atomicExch(err, 1); return; } // reference: max() of empty slice panics
+    float mx = wav_at(i_start), mn = mx;
+    for (long long i = i_start + 1; i < i_end; ++i) { const float v = wav_at(i); mx = fmaxf(mx, v); mn = fminf(mn, v); }
+    const float span = __fsub_rn(amp_max, amp_min);
+    long long top = (long long)roundf(__fdiv_rn(__fmul_rn(__fsub_rn(amp_max, mx), (float)nheight), span));
+    long long bottom = (long long)roundf(__fdiv_rn(__fmul_rn(__fsub_rn(amp_max, mn), (float)nheight), span));
+    if (bottom - top < 3) { // display.rs:100-105
+        const float d = (float)(3 - bottom + top);
+        const long long pad_bottom = (long long)ceilf(d / 2.0f), pad_top = (long long)floorf(d / 2.0f);
+        top -= pad_top; bottom += pad_bottom;
+    }
+    if (top < 0) top = 0;
+    if (bottom > nheight) bottom = nheight;
+    if (bottom + 1 > nheight) bottom = nheight - 1; // ndarray slice top..bottom+1 must stay inside
+    for (long long y = top; y <= bottom; ++y)
+        reinterpret_cast<uchar4 *>(out)[(size_t)y * nwidth + i_px] = make_uchar4(200, 21, 103, 255);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s)
+{
+    if (n_slots <= 0) return cudaSuccess;
+    range_init_kernel<<<(n_slots + 255) / 256, 256, 0, s>>>(slots, n_slots);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *out, cudaStream_t s)
+{
+    range_reduce_kernel<<<1, 256, 0, s>>>(slots, n_slots, out);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_range_commit(const float *max_negmin, float db_range, float *state,
+                                cudaStream_t s)
+{
+    range_commit_kernel<<<1, 1, 0, s>>>(max_negmin, db_range, state);
+    count_launch();
+    return cudaGetLastError();
+}
+
+uint32_t lanczos3_max_taps(uint32_t n_in, uint32_t n_out)
+{
+    const float ratio = (float)n_in / (float)n_out;
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    return (uint32_t)(2.0f * 3.0f * sratio) + 3;
+}
+
+cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_major, int *left,
+                                    int *cnt, float *sum, float *w, cudaStream_t s)
+{
+    build_axis_table_kernel<<<(n_out + 127) / 128, 128, 0, s>>>(n_in, n_out, taps, tap_major ? 1 : 0,
+                                                               left, cnt, sum, w);
+    count_launch();
+    return cudaGetLastError();
+}
+
+RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
+{
+    // frames a tile of px output columns needs, rows a tile of py output rows needs
+    const double rh = (double)width / nwidth, rv = (double)height / nheight;
+    const double sh = 3.0 * (rh < 1 ? 1 : rh), sv = 3.0 * (rv < 1 ? 1 : rv);
+    auto frames_for = [&](int px) { return (int)(px * rh + 2 * sh) + 4; };
+    auto rows_for = [&](int py) { return (int)(py * rv + 2 * sv) + 4; };
+    const size_t budget = 72 * 1024;
+    RenderTiling best{};
+    double best_cost = 1e300;
+    for (int px = 128; px >= 1; px >>= 1) {
+        if (px > 1 && px / 2 >= nwidth) continue;
+        for (int py = 256; py >= 1; py >>= 1) {
+            if (py > 1 && py / 2 >= nheight) continue;
+            if ((long)px * py > (long)kRenderThreads * kMaxPpt) continue;
+            int fc = frames_for(px);
+            const int rvm = rows_for(py);
+            if (fc > 96) fc = 64; // chunked accumulation for strong horizontal minification
+            const size_t smem = ((size_t)fc * (rvm | 1) + (size_t)py * (fc + 1)) * sizeof(float);
+            if (smem > budget) continue;
+            // cost per output pixel: redundant vertical work + redundant loads + underfilled threads
+            const double halo_h = (double)frames_for(px) / (px * rh), halo_v = (double)rows_for(py) / (py * rv);
+            double cost = halo_h * (1.0 + 0.5 * halo_v);
+            if (px * py < kRenderThreads * 4) cost *= 1.0 + (double)(kRenderThreads * 4) / (px * py) * 0.25;
+            if (px < 32) cost *= 1.0 + (32.0 / px - 1.0) * 0.5; // sub-line pixel stores
+            if (cost < best_cost) { best_cost = cost; best = RenderTiling{px, py, fc, rvm, smem}; }
+        }
+    }
+    if (best.px == 0) { // nothing fits: one pixel per tile, minimum chunk
+        const int rvm = rows_for(1);
+        int fc = 16;
+        while (fc > 1 && ((size_t)fc * (rvm | 1) + (fc + 1)) * sizeof(float) > 200 * 1024) fc >>= 1;
+        best = RenderTiling{1, 1, fc, rvm, ((size_t)fc * (rvm | 1) + (fc + 1)) * sizeof(float)};
+    }
+    return best;
+}
+
+cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight, size_t smem_bytes,
+                          cudaStream_t s)
+{
+    if (L.n_tracks <= 0 || max_nwidth <= 0 || max_nheight <= 0) return cudaSuccess;
+    static size_t configured = 48 * 1024;
+    if (smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured = smem_bytes;
+    }
+    dim3 grid((max_nwidth + L.px - 1) / L.px, (max_nheight + L.py - 1) / L.py, L.n_tracks);
+    render_kernel<<<grid, kRenderThreads, smem_bytes, s>>>(L);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_spec_to_grey(const float *spec, int n_frames, int n_out, int height, float max_db,
+                                float min_db, float *grey, cudaStream_t s)
+{
+    const size_t n = (size_t)n_frames * height;
+    if (n == 0) return cudaSuccess;
+    spec_to_grey_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(spec, n_frames, n_out, height,
+                                                                     max_db, min_db, grey);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_amp_to_db(float *x, size_t n, int *bad_flag, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    amp_to_db_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, bad_flag);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wav_image(const void *pcm, int fmt, int ch, long long n, int nwidth, int nheight,
+                             float amp_min, float amp_max, unsigned char *out, int *err_flag,
+                             cudaStream_t s)
+{
+    if (nwidth <= 0 || nheight <= 0) return cudaSuccess;
+    wav_image_kernel<<<(nwidth + 127) / 128, 128, 0, s>>>(pcm, fmt, ch, n, nwidth, nheight, amp_min,
+                                                         amp_max, out, err_flag);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace sgx

@@ -1,0 +1,679 @@
+// stft_kernel.cu -- K1, the fused analysis kernel (sm_100a).
+//
+// One launch turns PCM of a batch of tracks into their dB spectrograms:
+//   channel sum (lib.rs:42) -> reflect-padded framing (lib.rs:412-433, utils.rs:79-85) -> window,
+//   centred zero-pad (lib.rs:377-384) -> real FFT as an F/2-point complex FFT + split
+//   (realfft.rs:105-159) -> |X| (lib.rs:124) -> banded mel projection (lib.rs:131) -> dB
+//   (decibel.rs:33-88) -> per-track max/min (lib.rs:197-200).
+// Linear magnitudes and complex spectra never touch HBM in the dB modes.
+//
+// Layout of the work
+//   * a CTA owns a tile of consecutive frames of one track and stages the PCM samples those
+//     frames cover in shared memory ONCE: interior, mono, f32 tiles by a TMA bulk copy
+//     (cp.async.bulk + mbarrier), edge / stereo / int16 tiles by a reflecting gather;
+//   * a group of h/PTS threads transforms V frames at a time: every thread keeps PTS complex
+//     points of each of the V frames in registers, so index math and twiddles are shared by V
+//     frames and every shared-memory access is a V*4-byte vector;
+//   * Stockham autosort passes of radix PTS (then one pass of the remaining radix) exchange
+//     through a padded shared buffer (pad(e) = e + e/8 keeps the strided writes of the first pass
+//     conflict free for 128-bit accesses);
+//   * split / magnitude / mel / dB run on the same registers and buffer; dB rows go to HBM with
+//     coalesced stores, per-thread extrema are reduced to two atomics per CTA.
+#include <cstdint>
+#include <cstdio>
+
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace sgx {
+
+namespace {
+
+__device__ __forceinline__ int padi(int e) { return e + (e >> 3); }
+
+template <int V> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[V])
+{
+    if constexpr (V == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (V == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = *p;
+    }
+}
+template <int V> __device__ __forceinline__ void st_vec(float *p, const float (&v)[V])
+{
+    if constexpr (V == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (V == 2) {
+        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    } else {
+        *p = v[0];
+    }
+}
+
+// ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS) ----------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes,
+                                              unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---- sample access: channel sum + reflect (lib.rs:42, utils.rs:79-85) ---------------------------
+struct PcmView {
+    const void *pcm; long long n; int ch; int fmt;
+};
+__device__ __forceinline__ float load_sample(const PcmView &pv, long long i)
+{
+    if (i < 0) i = -i;                         // left reflect, edge sample not repeated
+    if (i >= pv.n) i = 2 * (pv.n - 1) - i;     // right reflect
+    i = i < 0 ? 0 : (i >= pv.n ? pv.n - 1 : i); // only reachable under zero window weight
+    float s = 0.0f;
+    if (pv.fmt == PCM_F32) {
+        const float *p = reinterpret_cast<const float *>(pv.pcm) + i * pv.ch;
+        for (int c = 0; c < pv.ch; ++c) s += __ldg(p + c);
+    } else {
+        const short *p = reinterpret_cast<const short *>(pv.pcm) + i * pv.ch;
+        for (int c = 0; c < pv.ch; ++c) s += (float)__ldg(p + c) * (1.0f / 32768.0f); // audio.rs:16-19
+    }
+    return s;
+}
+
+// ---- in-register DFT of R points at re[BASE + i*STRIDE], natural order in and out ----------------
+// cos/sin(2 pi k / 16)
+__device__ constexpr float kC16[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f,
+                                      0.38268343236508977f, 0.0f, -0.38268343236508977f,
+                                      -0.70710678118654752f, -0.92387953251128674f};
+__device__ constexpr float kS16[8] = {0.0f, 0.38268343236508977f, 0.70710678118654752f,
+                                      0.92387953251128674f, 1.0f, 0.92387953251128674f,
+                                      0.70710678118654752f, 0.38268343236508977f};
+
+template <int R, int BASE, int STRIDE, int PTS, int V>
+__device__ __forceinline__ void dft_inplace(float (&re)[PTS][V], float (&im)[PTS][V])
+{
+    if constexpr (R == 2) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float ar = re[BASE][v], ai = im[BASE][v];
+            const float br = re[BASE + STRIDE][v], bi = im[BASE + STRIDE][v];
+            re[BASE][v] = ar + br; im[BASE][v] = ai + bi;
+            re[BASE + STRIDE][v] = ar - br; im[BASE + STRIDE][v] = ai - bi;
+        }
+    } else if constexpr (R > 2) {
+        dft_inplace<R / 2, BASE, 2 * STRIDE, PTS, V>(re, im);          // even inputs
+        dft_inplace<R / 2, BASE + STRIDE, 2 * STRIDE, PTS, V>(re, im); // odd inputs
+        float tr[R][V], ti[R][V];
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+            constexpr int dummy = 0; (void)dummy;
+            const int e = BASE + 2 * k * STRIDE, o = BASE + (2 * k + 1) * STRIDE;
+            const int widx = k * (16 / R); // exp(-2 pi i k / R) = kC16[widx] - i kS16[widx]
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                float pr, pi;
+                if (widx == 0) { pr = re[o][v]; pi = im[o][v]; }
+                else if (widx == 4) { pr = im[o][v]; pi = -re[o][v]; }
+                else {
+                    const float c = kC16[widx], s = kS16[widx];
+                    pr = re[o][v] * c + im[o][v] * s;
+                    pi = im[o][v] * c - re[o][v] * s;
+                }
+                tr[k][v] = re[e][v] + pr; ti[k][v] = im[e][v] + pi;
+                tr[k + R / 2][v] = re[e][v] - pr; ti[k + R / 2][v] = im[e][v] - pi;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+#pragma unroll
+            for (int v = 0; v < V; ++v) { re[BASE + k * STRIDE][v] = tr[k][v]; im[BASE + k * STRIDE][v] = ti[k][v]; }
+    }
+}
+
+// ---- one Stockham pass of radix R with NS = product of the previous radices ----------------------
+// Thread `gt` of the group owns butterflies j = gt + q*NT, q < PTS/R.  Inputs of butterfly j are
+// elements j + r*H/R; outputs go to (j - k)*R + k + r*NS with k = j mod NS.  NS == 1 (first pass):
+// the caller has already put the inputs into the registers and no twiddle is needed.
+template <int H, int PTS, int V, int R, int NS>
+__device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V], float *sre,
+                                         float *sim, int gt, const float2 *__restrict__ tw)
+{
+    constexpr int NT = H / PTS, NB = PTS / R;
+    if constexpr (NS > 1) {
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int src = padi(gt + q * NT + r * (H / R)) * V;
+                ld_vec<V>(sre + src, re[q * R + r]);
+                ld_vec<V>(sim + src, im[q * R + r]);
+            }
+        __syncthreads(); // every thread has its inputs: the buffer may be overwritten
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int k = (gt + q * NT) & (NS - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                const float2 w = __ldg(tw + (r * k) * (H / (NS * R)));
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float xr = re[q * R + r][v], xi = im[q * R + r][v];
+                    re[q * R + r][v] = xr * w.x - xi * w.y;
+                    im[q * R + r][v] = xr * w.y + xi * w.x;
+                }
+            }
+        }
+    }
+    if constexpr (NB == 1) dft_inplace<R, 0, 1, PTS, V>(re, im);
+    else if constexpr (NB == 2) { dft_inplace<R, 0, 1, PTS, V>(re, im); dft_inplace<R, R, 1, PTS, V>(re, im); }
+    else if constexpr (NB == 4) {
+        dft_inplace<R, 0, 1, PTS, V>(re, im); dft_inplace<R, R, 1, PTS, V>(re, im);
+        dft_inplace<R, 2 * R, 1, PTS, V>(re, im); dft_inplace<R, 3 * R, 1, PTS, V>(re, im);
+    } else {
+        static_assert(NB == 8, "unsupported butterflies per thread");
+        dft_inplace<R, 0, 1, PTS, V>(re, im); dft_inplace<R, R, 1, PTS, V>(re, im);
+        dft_inplace<R, 2 * R, 1, PTS, V>(re, im); dft_inplace<R, 3 * R, 1, PTS, V>(re, im);
+        dft_inplace<R, 4 * R, 1, PTS, V>(re, im); dft_inplace<R, 5 * R, 1, PTS, V>(re, im);
+        dft_inplace<R, 6 * R, 1, PTS, V>(re, im); dft_inplace<R, 7 * R, 1, PTS, V>(re, im);
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int j = gt + q * NT;
+        const int k = j & (NS - 1);
+        const int d = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int dst = padi(d + r * NS) * V;
+            st_vec<V>(sre + dst, re[q * R + r]);
+            st_vec<V>(sim + dst, im[q * R + r]);
+        }
+    }
+    __syncthreads();
+}
+
+template <int H, int PTS, int V, int NS>
+__device__ __forceinline__ void run_passes(float (&re)[PTS][V], float (&im)[PTS][V], float *sre,
+                                           float *sim, int gt, const float2 *__restrict__ tw)
+{
+    if constexpr (NS < H) {
+        constexpr int R = (H / NS >= PTS) ? PTS : (H / NS);
+        fft_pass<H, PTS, V, R, NS>(re, im, sre, sim, gt, tw);
+        run_passes<H, PTS, V, NS * R>(re, im, sre, sim, gt, tw);
+    }
+}
+
+template <int LOG2H, int PTS, int V, int G> struct K1Traits {
+    static constexpr int H = 1 << LOG2H;
+    static constexpr int NT = H / PTS;
+    static constexpr int THREADS = G * NT;
+    static constexpr int PADH = ((H + (H >> 3) + 1) + 3) & ~3; // elements of V floats
+    static constexpr size_t FFT_SMEM = (size_t)G * 2 * PADH * V * sizeof(float);
+    static constexpr int MIN_CTAS = THREADS <= 256 ? 2 : 1;
+};
+
+template <int LOG2H, int PTS, int V, int G>
+__global__ void __launch_bounds__(K1Traits<LOG2H, PTS, V, G>::THREADS,
+                                  K1Traits<LOG2H, PTS, V, G>::MIN_CTAS)
+stft_db_kernel(const StftLaunch L)
+{
+    using TR = K1Traits<LOG2H, PTS, V, G>;
+    constexpr int H = TR::H, NT = TR::NT, THREADS = TR::THREADS, PADH = TR::PADH, F = 2 * H;
+    constexpr int R0 = PTS; // H >= PTS always for this kernel
+    static_assert(NT >= 32 && (NT % 32) == 0, "a group must be whole warps");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *tile = reinterpret_cast<float *>(smem_raw + 16);
+    float *fftbuf = tile + L.tile_floats;
+    __shared__ float red_max[32], red_min[32];
+
+    const int tid = threadIdx.x;
+    const int grp = tid / NT, gt = tid % NT;
+    float *sre = fftbuf + (size_t)grp * 2 * PADH * V;
+    float *sim = sre + PADH * V;
+
+    // ---- which track / tile ---------------------------------------------------------------------
+    const int tile_id = blockIdx.x;
+    int lo = 0, hi = L.n_tracks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (L.tracks[mid].tile_begin <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    const StftTrack *__restrict__ td = L.tracks + lo;
+    const PcmView pv{td->pcm, td->n, td->ch, td->fmt};
+    const int win = td->win, hop = td->hop, pad_l = td->pad_l, T = td->n_frames;
+    const float *__restrict__ win_f = td->win_f;
+    float *__restrict__ out = td->out;
+    const int n_out = td->n_out;
+    const int mode = L.mode;
+
+    const int t0 = (tile_id - td->tile_begin) * L.frames_per_tile;
+    const int nfr = min(L.frames_per_tile, T - t0);
+    const long long S0 = (long long)t0 * hop - win / 2 - pad_l; // first sample of frame t0 (FFT frame)
+    const int off0 = (int)(S0 & 3);
+    const long long A0 = S0 - off0; // 16-byte aligned start of the staged tile
+
+    // ---- stage the PCM tile ------------------------------------------------------------------------
+    if (L.staged) {
+        const int len = off0 + (nfr - 1) * hop + F;
+        const int len4 = (len + 3) & ~3;
+        const bool tma = pv.ch == 1 && pv.fmt == PCM_F32 &&
+                         ((reinterpret_cast<uintptr_t>(pv.pcm) & 15) == 0) && A0 >= 0 &&
+                         A0 + len4 <= pv.n;
+        if (tma) {
+            if (tid == 0) mbar_init(mbar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(mbar, (unsigned)len4 * 4u);
+                bulk_copy_g2s(tile, reinterpret_cast<const float *>(pv.pcm) + A0,
+                              (unsigned)len4 * 4u, mbar);
+            }
+            mbar_wait(mbar, 0);
+        } else {
+            for (int s = tid; s < len; s += THREADS) tile[s] = load_sample(pv, A0 + s);
+            __syncthreads();
+        }
+    }
+
+    float vmax = -INFINITY, vmin = INFINITY;
+    const int iters = L.frames_per_tile / (G * V);
+    for (int it = 0; it < iters; ++it) {
+        if (it * G * V >= nfr) break; // uniform
+        const int fl0 = (it * G + grp) * V; // first local frame of this group
+        float re[PTS][V], im[PTS][V];
+
+        // ---- first-pass inputs: z[m] = g[2m] + i g[2m+1], g = sample * window ---------------------
+#pragma unroll
+        for (int p = 0; p < PTS; ++p) {
+            const int m = gt + (p % R0) * (H / R0); // NB == 1 in the first pass
+            const int n = 2 * m;
+            const float2 w = __ldg(reinterpret_cast<const float2 *>(win_f + n));
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int fl = min(fl0 + v, nfr - 1);
+                float x0, x1;
+                if (L.staged) {
+                    const int b = off0 + fl * hop + n;
+                    x0 = tile[b]; x1 = tile[b + 1];
+                } else {
+                    const long long i = S0 + (long long)fl * hop + n;
+                    x0 = load_sample(pv, i); x1 = load_sample(pv, i + 1);
+                }
+                re[p][v] = x0 * w.x; im[p][v] = x1 * w.y;
+            }
+        }
+        run_passes<H, PTS, V, 1>(re, im, sre, sim, gt, L.tw);
+
+        // ---- real-FFT split (realfft.rs:140-157), pairs (k, h-k) --------------------------------------
+        constexpr int NP = PTS / 2;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int k = gt + q * NT;
+            const int kb = (H - k) & (H - 1);
+            ld_vec<V>(sre + padi(k) * V, re[q]);       ld_vec<V>(sim + padi(k) * V, im[q]);
+            ld_vec<V>(sre + padi(kb) * V, re[NP + q]); ld_vec<V>(sim + padi(kb) * V, im[NP + q]);
+        }
+        float cr[V], ci[V];
+        ld_vec<V>(sre + padi(H / 2) * V, cr); ld_vec<V>(sim + padi(H / 2) * V, ci);
+        __syncthreads(); // spectrum is in registers; the buffer is free for magnitudes
+
+        auto emit = [&](int idx, const float (&xr)[V], const float (&xi)[V]) {
+            if (mode == MODE_COMPLEX) {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (fl0 + v < nfr)
+                        reinterpret_cast<float2 *>(out)[(size_t)(t0 + fl0 + v) * (H + 1) + idx] =
+                            make_float2(xr[v], xi[v]);
+                return;
+            }
+            float mg[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) mg[v] = sqrtf(fmaf(xr[v], xr[v], xi[v] * xi[v])); // lib.rs:124
+            if (mode == MODE_MEL_DB) {
+                st_vec<V>(sre + padi(idx) * V, mg);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if (fl0 + v < nfr) {
+                        float y = mg[v];
+                        if (mode == MODE_LIN_DB) {
+                            y = amp_to_db_dev(y);
+                            vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+                        }
+                        out[(size_t)(t0 + fl0 + v) * (H + 1) + idx] = y;
+                    }
+                }
+            }
+        };
+
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int k = gt + q * NT;
+            const float2 cs = __ldg(L.split + k); // (cos, sin)(k pi / h)
+            float xr[V], xi[V], yr[V], yi[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float sumr = re[q][v] + re[NP + q][v], difr = re[q][v] - re[NP + q][v];
+                const float sumi = im[q][v] + im[NP + q][v], difi = im[q][v] - im[NP + q][v];
+                xr[v] = 0.5f * ((sumr + cs.x * sumi) - cs.y * difr);
+                xi[v] = 0.5f * ((difi - cs.y * sumi) - cs.x * difr);
+                yr[v] = 0.5f * ((sumr - cs.x * sumi) + cs.y * difr);
+                yi[v] = 0.5f * ((-difi - cs.y * sumi) - cs.x * difr);
+            }
+            emit(k, xr, xi);
+            emit(k == 0 ? H : H - k, yr, yi); // k == 0: the partner output is the Nyquist bin
+        }
+        if (gt == 0) {
+            float xi[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) xi[v] = -ci[v];
+            emit(H / 2, cr, xi);
+        }
+
+        // ---- banded mel projection + dB -----------------------------------------------------------
+        if (mode == MODE_MEL_DB) {
+            __syncthreads();
+            const int lg = td->mel_log2p, P = 1 << lg;
+            const int items = n_out << lg;
+            const int *__restrict__ mlo = td->mel_lo; const int *__restrict__ mcnt = td->mel_cnt;
+            const int *__restrict__ moff = td->mel_off; const float *__restrict__ mw = td->mel_w;
+            for (int w0 = 0; w0 < items; w0 += NT) {
+                const int wi = w0 + gt;
+                const int m = wi >> lg, pl = wi & (P - 1);
+                const bool valid = m < n_out;
+                const int blo = valid ? __ldg(mlo + m) : 0;
+                const int bcnt = valid ? __ldg(mcnt + m) : 0;
+                const int boff = valid ? __ldg(moff + m) : 0;
+                float acc[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+                for (int i = pl; i < bcnt; i += P) {
+                    const float wgt = __ldg(mw + boff + i);
+                    float mg[V];
+                    ld_vec<V>(sre + padi(blo + i) * V, mg);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[v] = fmaf(mg[v], wgt, acc[v]);
+                }
+                for (int s = P >> 1; s > 0; s >>= 1)
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], s);
+                if (valid && pl == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (fl0 + v < nfr) {
+                            const float y = amp_to_db_dev(acc[v]);
+                            vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+                            out[(size_t)(t0 + fl0 + v) * n_out + m] = y;
+                        }
+                }
+            }
+            __syncthreads(); // magnitudes consumed before the next iteration overwrites the buffer
+        }
+    }
+
+    // ---- per-track extrema (lib.rs:197-200) ----------------------------------------------------------
+    if (td->range_slot != nullptr && (mode == MODE_LIN_DB || mode == MODE_MEL_DB)) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
+        }
+        if ((tid & 31) == 0) { red_max[tid >> 5] = vmax; red_min[tid >> 5] = vmin; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < THREADS / 32; ++w) { vmax = fmaxf(vmax, red_max[w]); vmin = fminf(vmin, red_min[w]); }
+            if (vmax >= vmin) { // at least one value was produced
+                atomicMax(td->range_slot, enc_ordered(vmax));
+                atomicMin(td->range_slot + 1, enc_ordered(vmin));
+            }
+        }
+    }
+}
+
+// ---- small-F fallback: one CTA per frame, radix-2 Stockham, any power-of-two F >= 2 --------------------
+// Covers the reference's known-answer shapes (n_fft = 4, 256) and anything below the tuned sizes.
+__global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, int h)
+{
+    extern __shared__ __align__(16) float sm[];
+    float2 *a = reinterpret_cast<float2 *>(sm);
+    float2 *b = a + h;
+    float *mag = reinterpret_cast<float *>(b + h); // [h+1]
+    __shared__ float red_max[4], red_min[4];
+
+    const int tid = threadIdx.x;
+    const int tile_id = blockIdx.x;
+    int lo = 0, hi = L.n_tracks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (L.tracks[mid].tile_begin <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    const StftTrack *__restrict__ td = L.tracks + lo;
+    const PcmView pv{td->pcm, td->n, td->ch, td->fmt};
+    const int t = tile_id - td->tile_begin; // one frame per CTA
+    const int F = 2 * h, n_out = td->n_out, mode = L.mode;
+    const long long S0 = (long long)t * td->hop - td->win / 2 - td->pad_l;
+    float *__restrict__ out = td->out;
+
+    for (int m = tid; m < h; m += blockDim.x) {
+        const float w0 = td->win_f[2 * m], w1 = td->win_f[2 * m + 1];
+        a[m] = make_float2(load_sample(pv, S0 + 2 * m) * w0, load_sample(pv, S0 + 2 * m + 1) * w1);
+    }
+    __syncthreads();
+    for (int ns = 1; ns < h; ns <<= 1) {
+        for (int j = tid; j < h / 2; j += blockDim.x) {
+            const int k = j & (ns - 1);
+            float sn, cs;
+            sincospif(-(float)k / (float)ns, &sn, &cs); // exp(-2 pi i k / (2 ns))
+            const float2 u = a[j], x = a[j + h / 2];
+            const float2 v = make_float2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
+            const int d = (j - k) * 2 + k;
+            b[d] = make_float2(u.x + v.x, u.y + v.y);
+            b[d + ns] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+        float2 *tmp = a; a = b; b = tmp;
+    }
+    float vmax = -INFINITY, vmin = INFINITY;
+    for (int k = tid; k <= h; k += blockDim.x) {
+        float xr, xi;
+        if (k == h) { xr = a[0].x - a[0].y; xi = 0.0f; }  // realfft.rs:157
+        else {
+            const float2 p = a[k], q = a[(h - k) & (h - 1)];
+            float sn, cs;
+            sincospif((float)k / (float)h, &sn, &cs);
+            xr = 0.5f * (((p.x + q.x) + cs * (p.y + q.y)) - sn * (p.x - q.x));
+            xi = 0.5f * (((p.y - q.y) - sn * (p.y + q.y)) - cs * (p.x - q.x));
+        }
+        if (mode == MODE_COMPLEX) {
+            reinterpret_cast<float2 *>(out)[(size_t)t * (h + 1) + k] = make_float2(xr, xi);
+        } else {
+            const float mg = sqrtf(fmaf(xr, xr, xi * xi));
+            if (mode == MODE_MEL_DB) mag[k] = mg;
+            else {
+                float y = mg;
+                if (mode == MODE_LIN_DB) { y = amp_to_db_dev(y); vmax = fmaxf(vmax, y); vmin = fminf(vmin, y); }
+                out[(size_t)t * (h + 1) + k] = y;
+            }
+        }
+    }
+    if (mode == MODE_MEL_DB) {
+        __syncthreads();
+        for (int m = tid; m < n_out; m += blockDim.x) {
+            const int blo = td->mel_lo[m], bcnt = td->mel_cnt[m], boff = td->mel_off[m];
+            float acc = 0.0f;
+            for (int i = 0; i < bcnt; ++i) acc = fmaf(mag[blo + i], td->mel_w[boff + i], acc);
+            const float y = amp_to_db_dev(acc);
+            vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+            out[(size_t)t * n_out + m] = y;
+        }
+    }
+    (void)F;
+    if (td->range_slot != nullptr && (mode == MODE_LIN_DB || mode == MODE_MEL_DB)) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
+        }
+        if ((tid & 31) == 0) { red_max[tid >> 5] = vmax; red_min[tid >> 5] = vmin; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (int)blockDim.x / 32; ++w) { vmax = fmaxf(vmax, red_max[w]); vmin = fminf(vmin, red_min[w]); }
+            if (vmax >= vmin) {
+                atomicMax(td->range_slot, enc_ordered(vmax));
+                atomicMin(td->range_slot + 1, enc_ordered(vmin));
+            }
+        }
+    }
+}
+
+template <int LOG2H, int PTS, int V, int G>
+cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
+{
+    using TR = K1Traits<LOG2H, PTS, V, G>;
+    auto kern = stft_db_kernel<LOG2H, PTS, V, G>;
+    static size_t configured = 0; // per instantiation
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<L.n_tiles, TR::THREADS, smem, stream>>>(L);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace
+
+// FFT size -> kernel instantiation
+#define SGX_K1_TABLE(X) \
+    X(8, 8, 4, 8)       \
+    X(9, 8, 4, 4)       \
+    X(10, 8, 4, 2)      \
+    X(11, 8, 4, 1)      \
+    X(12, 8, 4, 1)      \
+    X(13, 8, 2, 1)
+
+bool stft_config_for(size_t n_fft, StftConfig *cfg)
+{
+    if (n_fft < 2 || (n_fft & (n_fft - 1)) != 0 || n_fft > 16384) return false;
+    const int h = (int)(n_fft / 2);
+    cfg->n_fft = (int)n_fft; cfg->h = h; cfg->generic = true;
+    cfg->pts = 2; cfg->vec = 1; cfg->groups = 1; cfg->threads = 128;
+    cfg->fft_smem = (size_t)(2 * h) * sizeof(float2) + (size_t)(h + 1) * sizeof(float);
+#define X(LG, PTS, V, G)                                              \
+    if (h == (1 << LG)) {                                             \
+        using TR = K1Traits<LG, PTS, V, G>;                           \
+        cfg->generic = false; cfg->pts = PTS; cfg->vec = V; cfg->groups = G; \
+        cfg->threads = TR::THREADS; cfg->fft_smem = TR::FFT_SMEM;     \
+    }
+    SGX_K1_TABLE(X)
+#undef X
+    return true;
+}
+
+size_t stft_max_dynamic_smem() { return 227 * 1024; }
+
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop)
+{
+    StftTiling t{};
+    if (cfg.generic) {
+        t.frames_per_tile = 1; t.staged = 0; t.tile_floats = 0;
+        t.smem_bytes = cfg.fft_smem;
+        return t;
+    }
+    const int unit = cfg.groups * cfg.vec;
+    // target two resident CTAs per SM for <= 256-thread CTAs, one otherwise
+    const size_t budget = (cfg.threads <= 256 ? (size_t)113 * 1024 : stft_max_dynamic_smem()) - 1024;
+    const size_t avail = budget > cfg.fft_smem + 16 ? budget - cfg.fft_smem - 16 : 0;
+    const long cap_floats = (long)(avail / sizeof(float));
+    // floats(nfr) = 3 + (nfr-1)*hop + F, rounded up to 4
+    int best = 0;
+    for (int mult = 1; mult <= 8; ++mult) {
+        const int nfr = unit * mult;
+        const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
+        if (need <= cap_floats) best = nfr;
+    }
+    if (best == 0) {
+        t.frames_per_tile = unit; t.staged = 0; t.tile_floats = 0;
+    } else {
+        // prefer >= 16 frames (amortises the halo) but do not shrink what fits
+        t.frames_per_tile = best; t.staged = 1;
+        long need = 3 + (long)(best - 1) * max_hop + cfg.n_fft;
+        t.tile_floats = (int)((need + 3) & ~3L) + 4;
+    }
+    t.smem_bytes = 16 + (size_t)t.tile_floats * sizeof(float) + cfg.fft_smem;
+    return t;
+}
+
+void make_fft_tables(int h, float2 *tw, float2 *split)
+{
+    const double pi = 3.14159265358979323846264338327950288;
+    for (int j = 0; j < h; ++j) {
+        const double a = -2.0 * pi * (double)j / (double)h;
+        tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int k = 0; k <= h / 2; ++k) {
+        const double a = pi * (double)k / (double)h;
+        split[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
+cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t stream)
+{
+    if (L.n_tiles <= 0) return cudaSuccess;
+    const size_t smem = cfg.generic ? cfg.fft_smem
+                                    : 16 + (size_t)L.tile_floats * sizeof(float) + cfg.fft_smem;
+    if (cfg.generic) {
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(stft_generic_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        stft_generic_kernel<<<L.n_tiles, 128, smem, stream>>>(L, cfg.h);
+        count_launch();
+        return cudaGetLastError();
+    }
+#define X(LG, PTS, V, G) \
+    if (cfg.h == (1 << LG)) return launch_one<LG, PTS, V, G>(L, smem, stream);
+    SGX_K1_TABLE(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+} // namespace sgx
