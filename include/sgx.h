@@ -192,6 +192,11 @@ SGX_API int sgx_mt_commit_range_device(sgx_multitrack *mt);
 /* max sample rate across ALL shards (lib.rs:220-224 is metadata-only; the driver max-reduces it
  * on the host before the first render).  0 = use the local maximum. */
 SGX_API int sgx_mt_set_global_max_sr(sgx_multitrack *mt, uint32_t max_sr);
+/* Stage timing for bench.py's roofline: when enabled, CUDA events bracket the K1 (analysis) launches
+ * of the most recent add_tracks call and the K3 (render) launches of the most recent image call on
+ * the handle's stream.  get_stage_times synchronises; -1 = nothing recorded. */
+SGX_API int sgx_mt_set_profiling(sgx_multitrack *mt, int on);
+SGX_API int sgx_mt_get_stage_times(sgx_multitrack *mt, float *analysis_ms, float *render_ms);
 /* Blocks until everything enqueued on the handle's stream has finished; refreshes the host
  * copies of max_db/min_db and reports `changed` (lib.rs:210-229) if non-NULL. */
 SGX_API int sgx_mt_synchronize(sgx_multitrack *mt, int *changed);

@@ -100,6 +100,8 @@ PROTOTYPES = {
     "sgx_mt_range_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
     "sgx_mt_commit_range_device": (C.c_int, [_vp]),
     "sgx_mt_set_global_max_sr": (C.c_int, [_vp, _u32]),
+    "sgx_mt_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "sgx_mt_get_stage_times": (C.c_int, [_vp, _pf, _pf]),
     "sgx_mt_synchronize": (C.c_int, [_vp, _pi]),
     "sgx_calc_proper_n_fft": (_sz, [_sz]),
     "sgx_track_params": (C.c_int, [_u32, C.POINTER(Settings), _psz, _psz, _psz]),
@@ -474,6 +476,15 @@ class MultiTrack:
 
     def set_global_max_sr(self, max_sr: int) -> None:
         _check(_lib.sgx_mt_set_global_max_sr(self._h, max_sr))
+
+    def set_profiling(self, on: bool) -> None:
+        _check(_lib.sgx_mt_set_profiling(self._h, int(on)))
+
+    def stage_times(self):
+        """(analysis_ms, render_ms) of the most recent add / render calls (CUDA events on the stream)."""
+        a, r = C.c_float(), C.c_float()
+        _check(_lib.sgx_mt_get_stage_times(self._h, C.byref(a), C.byref(r)))
+        return a.value, r.value
 
     def synchronize(self) -> bool:
         ch = C.c_int()

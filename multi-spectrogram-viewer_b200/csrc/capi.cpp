@@ -168,8 +168,7 @@ static int spec_image_host(sgx_multitrack *mt, size_t id, float px_per_sec, uint
         if (written) *written = need;
         if (!out) return;
         if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
-        std::vector<uint8_t> img = mt->impl.render_host(id, px_per_sec, nheight, channels);
-        if (!img.empty()) std::memcpy(out, img.data(), img.size());
+        mt->impl.render_host(id, px_per_sec, nheight, channels, out, need);
     });
 }
 
@@ -318,6 +317,17 @@ int sgx_mt_commit_range_device(sgx_multitrack *mt)
 int sgx_mt_set_global_max_sr(sgx_multitrack *mt, uint32_t max_sr)
 {
     return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->impl.set_global_max_sr(max_sr); });
+}
+int sgx_mt_set_profiling(sgx_multitrack *mt, int on)
+{
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->impl.set_profiling(on != 0); });
+}
+int sgx_mt_get_stage_times(sgx_multitrack *mt, float *analysis_ms, float *render_ms)
+{
+    return guarded([&] {
+        REQUIRE(mt && analysis_ms && render_ms, "NULL argument");
+        mt->impl.stage_times(analysis_ms, render_ms);
+    });
 }
 int sgx_mt_synchronize(sgx_multitrack *mt, int *changed)
 {

@@ -150,6 +150,7 @@ MultiTrack::~MultiTrack()
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
     tracks_.clear(); tables_.clear(); axis_.clear();
+    for (auto &e : ev_) if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(stream_);
 }
 
@@ -278,8 +279,11 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
     // ---- insert tracks (lib.rs:174-187) --------------------------------------------------------------
     for (size_t i = 0; i < ids.size(); ++i) {
         const PcmSource &s = srcs[i];
-        drop_track(ids[i]); // HashMap::insert replaces an existing id
-        Track t;
+        // HashMap::insert replaces an existing id; its device buffers and range slot are re-used
+        // (all work is ordered on one stream, so no synchronisation is needed for that)
+        auto it = tracks_.find(ids[i]);
+        if (it == tracks_.end()) it = tracks_.emplace(ids[i], Track()).first;
+        Track &t = it->second;
         t.path = s.path; t.sr = s.sr; t.ch = s.ch; t.fmt = s.fmt; t.n = s.n;
         t.win = pre[i].win; t.hop = pre[i].hop; t.n_fft = pre[i].n_fft;
         t.tables = tables_for(s.sr, t.win, t.n_fft);
@@ -287,18 +291,16 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         if (s.on_device) t.d_pcm = s.data;
         else {
             const size_t bytes = s.n * s.ch * esz;
-            t.owned_pcm.alloc(bytes + 64);
+            t.owned_pcm.ensure(bytes + 64);
             SGX_CUDA(cudaMemcpyAsync(t.owned_pcm.p, s.data, bytes, cudaMemcpyHostToDevice, stream_));
             t.d_pcm = t.owned_pcm.p;
         }
         t.n_frames = (size_t)pre[i].T;
         t.n_out = t.tables->n_mel ? t.tables->n_mel : t.n_fft / 2 + 1;
-        t.spec.alloc(t.n_frames * t.n_out);
-        t.slot = alloc_slot();
+        t.spec.ensure(t.n_frames * t.n_out);
+        if (t.slot < 0) t.slot = alloc_slot();
         const float sec = (float)t.n / (float)t.sr; // lib.rs:178-182
         if (sec > max_sec_) { max_sec_ = sec; id_max_sec_ = ids[i]; }
-        tracks_.erase(ids[i]);
-        tracks_.emplace(ids[i], std::move(t));
     }
     // ---- update_specs (lib.rs:142-168): one K1 launch per FFT size -------------------------------------
     std::map<size_t, std::vector<size_t>> by_fft;
@@ -327,6 +329,8 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
     }
     d_stft_.ensure(descs.size());
     SGX_CUDA(cudaMemcpyAsync(d_stft_.p, descs.data(), sizeof(StftTrack) * descs.size(), cudaMemcpyHostToDevice, stream_));
+    SGX_CUDA(launch_range_reset(d_stft_.p, (int)descs.size(), stream_)); // extrema of re-analysed tracks start over
+    if (profiling_) SGX_CUDA(cudaEventRecord(ev_[0], stream_));
     for (const Group &g : groups) {
         FftPlan &pl = ctx_->plan(g.n_fft);
         StftLaunch L{};
@@ -336,6 +340,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         L.tile_floats = g.tiling.tile_floats; L.tw = pl.tw.p; L.split = pl.split.p;
         SGX_CUDA(launch_stft(pl.cfg, L, stream_));
     }
+    if (profiling_) { SGX_CUDA(cudaEventRecord(ev_[1], stream_)); ev_valid_[0] = true; }
     // ---- update_spec_greys, range part (lib.rs:193-229) ------------------------------------------------
     reduce_and_commit(want_changed);
     uint32_t msr = 0;
@@ -449,6 +454,7 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
         for (const Item &it : items) sorted.push_back(descs[it.idx]);
         d_render_.ensure(sorted.size());
         SGX_CUDA(cudaMemcpyAsync(d_render_.p, sorted.data(), sizeof(RenderTrack) * sorted.size(), cudaMemcpyHostToDevice, stream_));
+        if (profiling_) SGX_CUDA(cudaEventRecord(ev_[2], stream_));
         size_t a = 0;
         while (a < items.size()) {
             size_t b = a + 1;
@@ -464,24 +470,35 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
             }
             a = b;
         }
+        if (profiling_) { SGX_CUDA(cudaEventRecord(ev_[3], stream_)); ev_valid_[1] = true; }
     }
     if (short_buf) throw Error(SGX_ERR_BUFFER, "output buffer too small");
 }
 
-std::vector<uint8_t> MultiTrack::render_host(size_t id, float px_per_sec, uint32_t nheight, int channels)
+void MultiTrack::render_host(size_t id, float px_per_sec, uint32_t nheight, int channels, uint8_t *out, size_t need)
 {
-    const Track &t = track(id);
-    const size_t need = (size_t)calc_nwidth(px_per_sec, t.n, t.sr) * nheight * channels;
-    std::vector<uint8_t> host(need);
-    if (need == 0) return host;
-    DevBuf<uint8_t> d;
-    d.alloc(need);
-    uint8_t *outs[1] = {d.p};
+    if (need == 0) return;
+    d_img_.ensure(need);
+    uint8_t *outs[1] = {d_img_.p};
     size_t caps[1] = {need}, wr[1] = {0};
     render({id}, px_per_sec, nheight, channels, outs, caps, wr);
-    SGX_CUDA(cudaMemcpyAsync(host.data(), d.p, need, cudaMemcpyDeviceToHost, stream_));
+    SGX_CUDA(cudaMemcpyAsync(out, d_img_.p, need, cudaMemcpyDeviceToHost, stream_));
     SGX_CUDA(cudaStreamSynchronize(stream_));
-    return host;
+}
+
+void MultiTrack::set_profiling(bool on)
+{
+    if (on && !ev_[0]) for (auto &e : ev_) SGX_CUDA(cudaEventCreate(&e));
+    profiling_ = on;
+    ev_valid_[0] = ev_valid_[1] = false;
+}
+
+void MultiTrack::stage_times(float *analysis_ms, float *render_ms)
+{
+    SGX_CUDA(cudaStreamSynchronize(stream_));
+    *analysis_ms = *render_ms = -1.0f;
+    if (ev_valid_[0]) SGX_CUDA(cudaEventElapsedTime(analysis_ms, ev_[0], ev_[1]));
+    if (ev_valid_[1]) SGX_CUDA(cudaEventElapsedTime(render_ms, ev_[2], ev_[3]));
 }
 
 std::vector<uint8_t> MultiTrack::wav_image(size_t id, float px_per_sec, uint32_t nheight, float amp_min, float amp_max)

@@ -45,7 +45,7 @@ template <class T> struct DevBuf {
         if (e != cudaSuccess) { cudaGetLastError(); throw Error(SGX_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)); }
         p = static_cast<T *>(q); n = count;
     }
-    void ensure(size_t count) { if (count > n) alloc(count + count / 4); }
+    void ensure(size_t count) { if (count > n) alloc(count); }
     void upload(const T *h, size_t count, cudaStream_t s)
     {
         if (count > n) alloc(count);
@@ -115,7 +115,9 @@ public:
     // lib.rs:294-298 (channels 3) / RGBA; device output, asynchronous
     void render(const std::vector<size_t> &ids, float px_per_sec, uint32_t nheight, int channels,
                 uint8_t *const *d_out, const size_t *cap, size_t *written);
-    std::vector<uint8_t> render_host(size_t id, float px_per_sec, uint32_t nheight, int channels);
+    void render_host(size_t id, float px_per_sec, uint32_t nheight, int channels, uint8_t *out, size_t need);
+    void set_profiling(bool on);
+    void stage_times(float *analysis_ms, float *render_ms);
     std::vector<uint8_t> wav_image(size_t id, float px_per_sec, uint32_t nheight, float amp_min, float amp_max);
 
     const Track &track(size_t id) const;
@@ -155,6 +157,9 @@ private:
     DevBuf<float> d_state_;  // {max_db, min_db, changed flag}  sticky like lib.rs:210-218
     DevBuf<StftTrack> d_stft_;
     DevBuf<RenderTrack> d_render_;
+    DevBuf<uint8_t> d_img_;      // staging for host-buffer image requests
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool profiling_ = false, ev_valid_[2] = {false, false};
     float max_db_, min_db_;
     float max_sec_ = 0.0f;
     size_t id_max_sec_ = 0;

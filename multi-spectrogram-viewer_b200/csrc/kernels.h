@@ -34,6 +34,8 @@ void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);
 
 // K2: global dB range (lib.rs:193-209)
 cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s);
+// resets the range slot of every track of a K1 descriptor array to the identity of the reduce
+cudaError_t launch_range_reset(const StftTrack *descs, int n, cudaStream_t s);
 // reduces slots [n][2] -> local {max, -min}
 cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *local_max_negmin,
                                 cudaStream_t s);

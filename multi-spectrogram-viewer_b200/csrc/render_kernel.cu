@@ -29,6 +29,15 @@ __global__ void range_init_kernel(unsigned *slots, int n)
     }
 }
 
+__global__ void range_reset_kernel(const StftTrack *__restrict__ descs, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && descs[i].range_slot != nullptr) {
+        descs[i].range_slot[0] = enc_ordered(-INFINITY);
+        descs[i].range_slot[1] = enc_ordered(INFINITY);
+    }
+}
+
 __global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, float *out)
 {
     __shared__ float smax[32], smin[32];
@@ -331,6 +340,13 @@ cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s)
 {
     if (n_slots <= 0) return cudaSuccess;
     range_init_kernel<<<(n_slots + 255) / 256, 256, 0, s>>>(slots, n_slots);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_range_reset(const StftTrack *descs, int n, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    range_reset_kernel<<<(n + 127) / 128, 128, 0, s>>>(descs, n);
     count_launch();
     return cudaGetLastError();
 }

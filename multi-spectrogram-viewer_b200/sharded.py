@@ -70,25 +70,29 @@ class ShardedMultiTrack:
         self.torch = torch
         self.group = group
         self.device = torch.cuda.current_device() if device is None else device
-        # run on torch's current stream so NCCL work and our kernels are ordered without host syncs
-        self.stream = torch.cuda.current_stream(self.device)
+        # one torch-owned stream carries our kernels AND the NCCL collective, so they are ordered on the
+        # device without any host synchronisation
+        self.stream = torch.cuda.Stream(device=self.device)
         self.mt = MultiTrack(settings, device=self.device, stream=self.stream.cuda_stream)
         self._range = torch.as_tensor(_DevicePtrView(self.mt.range_device_ptr(), 2), device=f"cuda:{self.device}")
 
     def add_tracks_device(self, id_list: Sequence[int], ptrs: Sequence[int], n_samples: Sequence[int], sr: Sequence[int],
                           channels: Optional[Sequence[int]] = None, keepalive=None, exchange_max_sr: bool = True) -> None:
         """Analysis of the local shard + the global range exchange; asynchronous."""
+        self.stream.wait_stream(self.torch.cuda.current_stream(self.device))  # inputs produced on the caller's stream
         self.mt.add_tracks_device(id_list, ptrs, n_samples, sr, channels, keepalive=keepalive, sync=False)
         if exchange_max_sr:
             local = max([int(s) for s in sr], default=0)
             self.mt.set_global_max_sr(all_reduce_max_sr(local, self.group, device=f"cuda:{self.device}"))
-        all_reduce_range(self._range, self.group)  # NCCL, 8 bytes, on the engine's stream
+        with self.torch.cuda.stream(self.stream):
+            all_reduce_range(self._range, self.group)  # NCCL, 8 bytes, ordered on the engine's stream
         self.mt.commit_range_device()
 
     def remove_track(self, id: int, owned: bool) -> None:
         if owned:
             self.mt.remove_track(id, sync=False)
-        all_reduce_range(self._range, self.group)
+        with self.torch.cuda.stream(self.stream):
+            all_reduce_range(self._range, self.group)
         self.mt.commit_range_device()
 
     def render_device(self, id_list, px_per_sec, nheight, channels, out_ptrs, caps) -> None:

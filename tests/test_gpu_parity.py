@@ -1,0 +1,336 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Tolerances are north_star's:
+magnitudes 1e-4 relative (to the frame's peak), dB 1e-3 (above the display floor), pixels +-1 LSB."""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+NAMES = ["8k", "16k", "22k05", "24k", "44k1"]
+
+MAG_RTOL = 1e-4   # |dX| <= MAG_RTOL * max_k |X_ref[frame]|
+DB_ATOL = 1e-3    # dB, for values above (max - 120 dB)
+PX_LSB = 1        # RGBA bytes
+
+
+def impulse(n, loc):
+    x = np.zeros(n, np.float32)
+    x[loc] = 1.0
+    return x
+
+
+def frame_rel_err(got, ref):
+    peak = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-30)
+    return float((np.abs(got - ref) / peak).max())
+
+
+def db_err(got, ref, floor_db=120.0):
+    keep = ref > (ref.max() - floor_db)
+    return float(np.abs(got - ref)[keep].max())
+
+
+# ---- reference KATs through the GPU ---------------------------------------------------------------
+def test_stft_works_kat(msv):
+    """lib.rs:491-514"""
+    got = msv.perform_stft(impulse(4, 2), 4, 2, 4)
+    want = np.array([[0, 0, 0], [0.25, -0.25, 0.25], [0.25, -0.25, 0.25]], np.complex64)
+    assert got.shape == (3, 3)
+    assert np.max(np.abs(got - want)) <= 1e-7
+
+
+def test_rfft_impulse_kat(msv):
+    """utils.rs:117-123 rfft(impulse) == all ones: frame 0 of an impulse placed where the left reflect
+    puts it at sample 0 of the frame, rectangular window."""
+    x = impulse(64, 32)
+    got = msv.perform_stft(x, 64, 64, 64, window=np.ones(64, np.float32))
+    assert got.shape == (2, 33)
+    assert np.max(np.abs(got[0] - 1.0)) <= 1e-6
+
+
+def test_real_to_complex_kat(msv, orc):
+    """realfft.rs:253-272 shape (n_fft=256) against the f64 truth."""
+    x = np.zeros(256 * 3, np.float32)
+    x[1 + 256] = 1.0
+    x[3 + 256] = 0.5
+    got = msv.perform_stft(x, 256, 128, 256, window=np.ones(256, np.float32))
+    truth = orc.stft_mag_f64(x, 256, 128, 256, window=np.ones(256, np.float32))
+    assert np.max(np.abs(np.abs(got) - truth)) <= 2e-6
+
+
+# ---- STFT / magnitude parity over sizes -------------------------------------------------------------
+STFT_CASES = [
+    # (n, win, hop, n_fft)
+    (4000, 4, 2, 4), (3000, 6, 3, 8), (5000, 30, 7, 32), (9000, 128, 32, 128), (9000, 200, 50, 256),
+    (20000, 320, 80, 512), (20000, 512, 128, 512), (30000, 640, 160, 1024), (30000, 884, 221, 1024),
+    (60000, 1764, 441, 2048), (60000, 1920, 480, 2048), (60000, 2048, 512, 2048), (90000, 4096, 256, 4096),
+    (90000, 3000, 1000, 4096), (150000, 8192, 2048, 8192), (200000, 16384, 4096, 16384), (200000, 10000, 3333, 16384),
+    (2048, 2048, 512, 2048),      # shortest legal input: n == win
+    (2050, 2048, 2048, 2048),     # hop == win
+    (50000, 1024, 5000, 1024),    # hop > n_fft (tile staging cannot be used)
+]
+
+
+@pytest.mark.parametrize("n,win,hop,n_fft", STFT_CASES)
+def test_perform_stft_parity(msv, orc, n, win, hop, n_fft):
+    x = synth.base_clip(n, 16000, seed=n + win)
+    ref = orc.perform_stft(x, win, hop, n_fft)
+    got = msv.perform_stft(x, win, hop, n_fft)
+    assert got.shape == ref.shape
+    err = frame_rel_err(got, ref)
+    truth = orc.stft_mag_f64(x, win, hop, n_fft)
+    e_gpu = frame_rel_err(np.abs(got).astype(np.float64), truth)
+    e_ref = frame_rel_err(np.abs(ref).astype(np.float64), truth)
+    print(f"stft n_fft={n_fft} win={win} hop={hop}: gpu-vs-oracle {err:.2e}; vs f64 truth gpu {e_gpu:.2e} oracle {e_ref:.2e}")
+    assert err <= MAG_RTOL
+    mag = msv.stft_magnitude(x, win, hop, n_fft)
+    assert frame_rel_err(mag, np.abs(ref)) <= MAG_RTOL
+
+
+def test_custom_window_and_mismatch(msv, orc):
+    x = synth.base_clip(30000, 16000, seed=9)
+    w = (np.hamming(640) / 1024).astype(np.float32)
+    assert frame_rel_err(msv.perform_stft(x, 640, 160, 1024, window=w), orc.perform_stft(x, 640, 160, 1024, window=w)) <= MAG_RTOL
+    with pytest.raises(msv.SgxError) as e:   # assert_eq!(w.len(), win_length) lib.rs:404
+        msv.perform_stft(x, 640, 160, 1024, window=w[:-1])
+    assert e.value.code == msv.SGX_ERR_BAD_ARG
+    with pytest.raises(msv.SgxError):        # input shorter than the window: the reference panics on its slices
+        msv.perform_stft(x[:100], 640, 160, 1024)
+    with pytest.raises(msv.SgxError):        # n_fft not a power of two (Radix4)
+        msv.perform_stft(x, 600, 150, 1000)
+
+
+# ---- dB spectrograms ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("sr", [8000, 16000, 22050, 24000, 44100, 48000])
+def test_default_mel_db_parity(msv, orc, sr):
+    """MultiTrack defaults per sample rate (lib.rs:43-46, mel.rs:87-99)."""
+    win, hop, n_fft = msv.track_params(sr)
+    x = synth.base_clip(3 * sr + 17, sr, seed=sr)
+    fb = msv.calc_mel_fb_default(sr, n_fft)
+    ref = orc.calc_spec(x, win, hop, n_fft, None, fb)
+    got = msv.melspectrogram_db(x, win, hop, n_fft, None, fb)
+    assert got.shape == ref.shape
+    e = db_err(got, ref)
+    truth = orc.calc_spec_f64(x, win, hop, n_fft, None, fb)
+    print(f"mel dB sr={sr} M={fb.shape[1]}: gpu-vs-oracle {e:.2e} dB; vs truth gpu {db_err(got, truth):.2e} oracle {db_err(ref, truth):.2e}")
+    assert e <= DB_ATOL
+
+
+@pytest.mark.parametrize("n_fft,hop,n_mel,sr", [(2048, 512, 128, 44100), (4096, 256, 128, 48000), (512, 128, 128, 44100), (1024, 256, 64, 16000),
+                                                (8192, 2048, 128, 48000), (16384, 4096, 128, 48000), (256, 64, 40, 8000), (64, 16, 8, 8000)])
+def test_fixed_mel_db_parity(msv, orc, n_fft, hop, n_mel, sr):
+    x = synth.base_clip(max(4 * n_fft, 2 * sr), sr, seed=n_fft + n_mel)
+    fb = msv.calc_mel_fb(sr, n_fft, n_mel)
+    ref = orc.calc_spec(x, n_fft, hop, n_fft, None, fb)
+    got = msv.melspectrogram_db(x, n_fft, hop, n_fft, None, fb)
+    e = db_err(got, ref)
+    print(f"mel-{n_mel} n_fft={n_fft}: {e:.2e} dB")
+    assert e <= DB_ATOL
+    # empty filters (no bin inside) sit on the -360 dB floor in both
+    assert np.array_equal(got <= -359.0, ref <= -359.0)
+
+
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048, 4096, 8192, 16384])
+def test_linear_db_parity(msv, orc, n_fft):
+    """C4 shape: linear-frequency dB, hop = n_fft/4."""
+    x = synth.base_clip(6 * n_fft + 123, 44100, seed=n_fft)
+    ref = orc.calc_spec(x, n_fft, n_fft // 4, n_fft, None, None)
+    got = msv.melspectrogram_db(x, n_fft, n_fft // 4, n_fft, None, None)
+    e = db_err(got, ref)
+    print(f"linear dB n_fft={n_fft}: {e:.2e}")
+    assert e <= DB_ATOL
+
+
+def test_silence_hits_the_floor(msv, orc):
+    x = np.zeros(20000, np.float32)
+    got = msv.melspectrogram_db(x, 640, 160, 1024, None, msv.calc_mel_fb_default(16000, 1024))
+    assert np.all(got == -360.0)                       # decibel.rs:49-53 with amin = 1e-18
+    assert np.array_equal(msv.amp_to_db_default([0.0, 1e-19, 1.0, 10.0]), orc.amp_to_db_default([0.0, 1e-19, 1.0, 10.0]))
+    with pytest.raises(msv.SgxError):                  # decibel.rs:34
+        msv.amp_to_db_default([1.0, -1.0])
+
+
+def test_stereo_is_channel_sum(msv, orc):
+    """lib.rs:42 sums channels (no 1/2)."""
+    sr = 16000
+    l = synth.base_clip(2 * sr, sr, 1)
+    r = np.roll(l, 1234) * np.float32(0.75)
+    mt = msv.MultiTrack()
+    mt.add_tracks_pcm([0], [np.stack([l, r], axis=1)], [sr])
+    win, hop, n_fft = msv.track_params(sr)
+    ref = orc.calc_spec(l + r, win, hop, n_fft, None, msv.calc_mel_fb_default(sr, n_fft))
+    assert db_err(mt.get_spec_db(0), ref) <= DB_ATOL
+    mt.close()
+
+
+# ---- display stages -----------------------------------------------------------------------------------
+def test_spec_to_grey_parity(msv, orc):
+    rng = np.random.default_rng(0)
+    spec = (-150 + 130 * rng.random((300, 77))).astype(np.float32)
+    for up in (1.0, 1.3259, 1.70609):
+        got, ref = msv.spec_to_grey(spec, up, -20.0, -140.0), orc.spec_to_grey(spec, up, -20.0, -140.0)
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("shape,new", [((370, 440), (1000, 500)), ((438, 440), (1000, 500)), ((257, 2000), (300, 120)), ((64, 64), (64, 64)),
+                                       ((1025, 300), (300, 500)), ((40, 3000), (50, 10)), ((500, 100), (1, 1)), ((3, 5), (40, 30)),
+                                       ((8193, 64), (64, 500))])
+def test_grey_to_rgb_parity(msv, orc, shape, new):
+    """display.rs:56-61 incl. the per-pass clamp of image 0.23's resize; noisy content makes the clamp bite."""
+    rng = np.random.default_rng(shape[0] * 7 + new[0])
+    g = rng.random(shape).astype(np.float32) ** 3
+    g[rng.random(shape) < 0.3] = 0.0
+    for ch in (3, 4):
+        got, ref = msv.grey_to_rgb(g, new[0], new[1], ch), orc.grey_to_rgb(g, new[0], new[1], ch)
+        d = np.abs(got.astype(int) - ref.astype(int))
+        print(f"grey_to_rgb {shape}->{new} ch={ch}: max diff {d.max()}, mismatching bytes {(d > 0).mean():.2e}")
+        assert d.max() <= PX_LSB
+        assert (d > 0).mean() < 0.01
+        if ch == 4:
+            assert np.all(got[..., 3] == 255)
+
+
+# ---- MultiTrack: the public path ----------------------------------------------------------------------
+def _clips():
+    z = np.load(os.path.join(HERE, "golden", "clips.npz"))
+    return {k: (z[f"pcm_{k}"], int(z[f"sr_{k}"])) for k in NAMES}
+
+
+def test_multitrack_golden_clips(msv, orc):
+    """The reference's multitrack_works flow (lib.rs:516-546) on its own sample audio (first 2 s of each
+    fixture, int16 ingest), against the committed oracle outputs and the live oracle."""
+    clips = _clips()
+    exp = np.load(os.path.join(HERE, "golden", "expected.npz"))
+    mt = msv.MultiTrack()
+    assert mt.add_tracks_pcm(list(range(5)), [clips[k][0] for k in NAMES], [clips[k][1] for k in NAMES]) is True
+    assert abs(mt.get_max_db() - float(exp["max_db"])) <= DB_ATOL and abs(mt.get_min_db() - float(exp["min_db"])) <= DB_ATOL
+    for i, k in enumerate(NAMES):
+        spec = mt.get_spec_db(i)
+        assert tuple(exp[f"spec_shape_{k}"]) == spec.shape
+        sub, want = spec[::7, ::5], exp[f"spec_sub_{k}"]
+        keep = want > float(exp["max_db"]) - 120
+        assert np.abs(sub - want)[keep].max() <= 2 * DB_ATOL
+        img = mt.get_spec_image(i, 100.0, 120).reshape(120, -1, 3)
+        d = np.abs(img.astype(int) - exp[f"img_{k}"].astype(int))
+        print(f"golden image {k}: max diff {d.max()}, mismatching bytes {(d > 0).mean():.2e}")
+        assert img.shape == exp[f"img_{k}"].shape and d.max() <= PX_LSB
+        assert mt.get_sr(i) == clips[k][1] and abs(mt.get_sec(i) - 2.0) < 1e-6
+    assert mt.get_max_sec() == pytest.approx(2.0)
+    mt.close()
+
+
+def _oracle_batch(orc, msv, wavs, srs, settings=None, nheight=500, px=100.0, channels=3):
+    params = [msv.track_params(sr, settings) for sr in srs]
+    mel = settings is None or settings.freq_scale == msv.FREQ_MEL
+    windows = [orc.calc_window(p[0], p[2]) for p in params]
+    if not mel:
+        fbs = [None] * len(wavs)
+    elif settings is not None and settings.n_mel:
+        fbs = [orc.calc_mel_fb(sr, p[2], settings.n_mel) for sr, p in zip(srs, params)]
+    else:
+        fbs = [orc.calc_mel_fb_default(sr, p[2]) for sr, p in zip(srs, params)]
+    return orc.pipeline(wavs, srs, params, windows, fbs, mel_scale=mel, px_per_sec=px, nheight=nheight, channels=channels)
+
+
+def test_multitrack_six_rates_end_to_end(msv, orc):
+    """C2 shape: six sample rates, default settings, 100 px/s x 500 (bench.rs:57), RGB and RGBA."""
+    srs = [8000, 16000, 22050, 24000, 44100, 48000]
+    wavs = [synth.derive_track(synth.base_clip(int(3.3 * sr), sr, seed=sr), i) for i, sr in enumerate(srs)]
+    imgs, mx, mn = _oracle_batch(orc, msv, wavs, srs)
+    mt = msv.MultiTrack()
+    assert mt.add_tracks_pcm(list(range(6)), wavs, srs)
+    assert abs(mt.get_max_db() - mx) <= DB_ATOL and abs(mt.get_min_db() - mn) <= DB_ATOL
+    for i in range(6):
+        rgb = mt.get_spec_image(i, 100.0, 500).reshape(500, -1, 3)
+        d = np.abs(rgb.astype(int) - imgs[i].astype(int))
+        print(f"track {i} sr={srs[i]}: image {rgb.shape}, max diff {d.max()}, mismatching bytes {(d > 0).mean():.2e}")
+        assert rgb.shape == imgs[i].shape and d.max() <= PX_LSB and (d > 0).mean() < 0.01
+        rgba = mt.get_spec_image_rgba(i, 100.0, 500).reshape(500, -1, 4)
+        assert np.array_equal(rgba[..., :3], rgb) and np.all(rgba[..., 3] == 255)
+        assert mt.image_width(i, 100.0) == orc.calc_nwidth(100.0, wavs[i].size, srs[i])
+    mt.close()
+
+
+def test_multitrack_linear_and_fixed_mel(msv, orc):
+    srs = [44100, 22050]
+    wavs = [synth.base_clip(2 * sr, sr, seed=3 + sr) for sr in srs]
+    for settings in (msv.Settings.default(freq_scale=msv.FREQ_LINEAR, win_length=2048, hop_length=512, n_fft=2048),
+                     msv.Settings.default(n_mel=128, win_length=1024, hop_length=256, n_fft=1024)):
+        imgs, mx, mn = _oracle_batch(orc, msv, wavs, srs, settings, nheight=200, px=80.0, channels=4)
+        mt = msv.MultiTrack(settings)
+        mt.add_tracks_pcm([10, 20], wavs, srs)
+        assert abs(mt.get_max_db() - mx) <= DB_ATOL and abs(mt.get_min_db() - mn) <= DB_ATOL
+        for i, tid in enumerate([10, 20]):
+            got = mt.get_spec_image_rgba(tid, 80.0, 200).reshape(200, -1, 4)
+            d = np.abs(got.astype(int) - imgs[i].astype(int))
+            assert got.shape == imgs[i].shape and d.max() <= PX_LSB
+        mt.close()
+
+
+def test_multitrack_semantics(msv, orc):
+    """changed flags, re-normalisation on remove (lib.rs:265-292), getters, unknown ids."""
+    sr = 16000
+    base = synth.base_clip(2 * sr, sr, 5)
+    quiet, loud = base * np.float32(0.125), base
+    mt = msv.MultiTrack()
+    assert mt.add_tracks_pcm([1], [quiet], [sr]) is True
+    r1 = (mt.get_max_db(), mt.get_min_db())
+    img_before = mt.get_spec_image(1, 50.0, 64)
+    assert mt.add_tracks_pcm([2], [loud], [sr]) is True            # louder track moves the global max
+    assert mt.get_max_db() > r1[0] + 17.0
+    img_mid = mt.get_spec_image(1, 50.0, 64)
+    assert not np.array_equal(img_before, img_mid)                  # track 1 re-normalised
+    assert mt.add_tracks_pcm([3], [quiet], [sr]) is False           # range and max_sr unchanged (lib.rs:211-229)
+    assert mt.remove_track(3) is False
+    assert mt.remove_track(2) is True                                # back to the quiet range
+    assert (mt.get_max_db(), mt.get_min_db()) == pytest.approx(r1, abs=1e-6)
+    assert np.array_equal(mt.get_spec_image(1, 50.0, 64), img_before)
+    assert mt.get_frequency_hz(1, 1.0) == pytest.approx(sr / 2, rel=1e-5)
+    assert mt.get_frequency_hz(1, 0.5) == pytest.approx(msv.mel_to_hz(msv.hz_to_mel(sr / 2) * 0.5), rel=1e-6)
+    for call in (lambda: mt.get_spec_image(99, 50.0, 64), lambda: mt.remove_track(99), lambda: mt.get_sr(99)):
+        with pytest.raises(msv.SgxError) as e:
+            call()
+        assert e.value.code == msv.SGX_ERR_UNKNOWN_ID
+    with pytest.raises(msv.SgxError):                               # shorter than one window
+        mt.add_tracks_pcm([7], [base[:100]], [sr])
+    mt.close()
+
+
+def test_add_tracks_from_wav_files(msv, orc, tmp_path):
+    import wave
+
+    clips = _clips()
+    paths = []
+    for k in NAMES[:3]:
+        p = tmp_path / f"sample_{k}.wav"
+        with wave.open(str(p), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(clips[k][1]); w.writeframes(clips[k][0].tobytes())
+        paths.append(str(p))
+    mt, mt2 = msv.MultiTrack(), msv.MultiTrack()
+    assert mt.add_tracks([0, 1, 2], "\n".join(paths))
+    mt2.add_tracks_pcm([0, 1, 2], [clips[k][0].astype(np.float32) / np.float32(32768) for k in NAMES[:3]], [clips[k][1] for k in NAMES[:3]])
+    for i in range(3):
+        assert np.array_equal(mt.get_spec_db(i), mt2.get_spec_db(i))          # int16 ingest == f32 ingest, bit for bit
+        assert np.array_equal(mt.get_spec_image(i, 100.0, 100), mt2.get_spec_image(i, 100.0, 100))
+    assert mt.get_filename(1) == "sample_16k.wav" and mt.get_path(1) == paths[1]
+    with pytest.raises(msv.SgxError) as e:
+        mt.add_tracks([5, 6], paths[0] + "\n" + str(tmp_path / "nope.wav"))
+    assert e.value.code == msv.SGX_ERR_IO
+    with pytest.raises(msv.SgxError):
+        mt.get_sr(5)                                                            # atomic: nothing inserted
+    mt.close(); mt2.close()
+
+
+def test_wav_image_parity(msv, orc):
+    """display.rs:63-115 (get_wav_image)."""
+    sr = 8000
+    x = synth.base_clip(3 * sr, sr, 11) * np.float32(3.0)
+    for nw, nh, rng in [(300, 100, (-1.0, 1.0)), (24000 * 2, 64, (-1.0, 1.0)), (50, 40, (-0.5, 0.5))]:
+        assert np.array_equal(msv.wav_to_image(x, nw, nh, rng), orc.wav_to_image(x, nw, nh, *rng)), (nw, nh)
+    mt = msv.MultiTrack()
+    mt.add_tracks_pcm([0], [x], [sr])
+    got = mt.get_wav_image(0, 100.0, 100, -1.0, 1.0).reshape(100, 300, 4)
+    assert np.array_equal(got, orc.wav_to_image(x, 300, 100, -1.0, 1.0))
+    mt.close()

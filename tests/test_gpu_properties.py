@@ -1,0 +1,86 @@
+"""Size-independent properties at the full BASELINE sizes (where the CPU oracle would take minutes)."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def test_c5_track_properties(msv, orc):
+    """One C5 track (10 min, 48 kHz, defaults): frame count, gain linearity (+20log10 g dB exactly up to
+    rounding), time-shift covariance, image geometry; a 20 s window is checked against the oracle."""
+    sr, n = 48000, 600 * 48000
+    base = synth.base_clip(n, sr, 5005)
+    mt = msv.MultiTrack()
+    g = np.float32(0.5)
+    mt.add_tracks_pcm([0, 1], [base, base * g], [sr, sr])
+    T, M = mt.spec_shape(0)
+    assert (T, M) == (n // 480 + 1, 347)
+    a, b = mt.get_spec_db(0), mt.get_spec_db(1)
+    assert np.abs((a - b) - np.float32(20 * np.log10(2.0))).max() <= 1e-3          # linearity
+    win, hop, n_fft = msv.track_params(sr)
+    fb = msv.calc_mel_fb_default(sr, n_fft)
+    seg = slice(5_000_000, 5_000_000 + 20 * sr)
+    ref = orc.calc_spec(base[seg], win, hop, n_fft, None, fb)
+    f0 = seg.start // hop                                                            # seg.start is a multiple of hop
+    inner = slice(8, ref.shape[0] - 8)                                               # frames not touching the segment's reflect edges
+    assert np.abs(a[f0:f0 + ref.shape[0]][inner] - ref[inner]).max() <= 1e-3
+    assert mt.image_width(0, 100.0) == 60000
+    img = mt.get_spec_image_rgba(0, 100.0, 500).reshape(500, 60000, 4)
+    assert img[..., 3].min() == 255 and img[..., :3].std() > 10
+    mt.close()
+
+
+def test_c3_stereo_properties(msv, orc):
+    """C3 shape (48 kHz stereo, n_fft 4096, hop 256, mel-128) on 2 minutes: L+R sum, frame count, a window vs the oracle."""
+    sr, n = 48000, 120 * 48000
+    l = synth.base_clip(n, sr, 3003)
+    r = np.roll(l, 1234) * np.float32(0.75)
+    s = msv.Settings.default(win_length=4096, hop_length=256, n_fft=4096, n_mel=128)
+    mt = msv.MultiTrack(s)
+    mt.add_tracks_pcm([0], [np.stack([l, r], axis=1)], [sr])
+    T, M = mt.spec_shape(0)
+    assert (T, M) == (n // 256 + 1, 128)
+    a = mt.get_spec_db(0)
+    fb = msv.calc_mel_fb(sr, 4096, 128)
+    start = 256 * 9000
+    ref = orc.calc_spec((l + r)[start:start + 5 * sr], 4096, 256, 4096, None, fb)
+    inner = slice(16, ref.shape[0] - 16)
+    assert np.abs(a[9000:9000 + ref.shape[0]][inner] - ref[inner]).max() <= 1e-3
+    w = mt.image_width(0, 100.0)
+    img = mt.get_spec_image(0, 100.0, 500)
+    assert img.size == w * 500 * 3 and w == 12000
+    mt.close()
+
+
+def test_device_resident_batch_matches_host_path(msv):
+    """The bench's `value` path (PCM resident in HBM, deferred range, batched device render) produces the same
+    bytes as the public host-buffer path."""
+    torch = _torch()
+    sr = 48000
+    base = synth.base_clip(20 * sr, sr, 42)
+    tracks = [synth.derive_track(base, t) for t in range(4)]
+    mt = msv.MultiTrack()
+    mt.add_tracks_pcm(list(range(4)), tracks, [sr] * 4)
+    want = [mt.get_spec_image_rgba(i, 100.0, 500) for i in range(4)]
+    rng_want = (mt.get_max_db(), mt.get_min_db())
+    mt.close()
+
+    dev = [torch.from_numpy(t).cuda() for t in tracks]
+    sm = msv.ShardedMultiTrack()
+    sm.add_tracks_device(list(range(4)), [d.data_ptr() for d in dev], [d.numel() for d in dev], [sr] * 4, keepalive=dev)
+    w = sm.mt.image_width(0, 100.0)
+    outs = [torch.empty(w * 500 * 4, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    sm.render_device(list(range(4)), 100.0, 500, 4, [o.data_ptr() for o in outs], [o.numel() for o in outs])
+    assert sm.synchronize() is True
+    assert (sm.get_max_db(), sm.get_min_db()) == rng_want
+    for o, wv in zip(outs, want):
+        assert np.array_equal(o.cpu().numpy(), wv)
+    sm.close()
