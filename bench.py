@@ -307,6 +307,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c1"])
+    ap.add_argument("--tracks", type=int, default=0, help="override tracks per GPU (profiling runs only)")
+    ap.add_argument("--seconds", type=float, default=0, help="override track length (profiling runs only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -314,6 +316,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = workload(args.workload)
+    if args.tracks:
+        wl["tracks"] = args.tracks; wl["desc"] += f" [OVERRIDE tracks={args.tracks}: not a headline run]"
+    if args.seconds:
+        wl["seconds"] = args.seconds; wl["desc"] += f" [OVERRIDE seconds={args.seconds}: not a headline run]"
     cfg = {"workload": wl["desc"], "px_per_sec": PX_PER_SEC, "nheight": NHEIGHT,
            "l2": "inputs larger than L2: every step streams the whole PCM batch and writes every pixel (GBs per step vs 126 MB L2)"
                  if args.workload != "c1" else "C1 fits in L2; not a headline number",

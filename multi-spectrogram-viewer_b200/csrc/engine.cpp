@@ -466,7 +466,7 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
                 L.tracks = d_render_.p + c; L.n_tracks = (int)std::min<size_t>(65535, b - c);
                 L.from_db = 1; L.range = d_state_.p; L.channels = channels;
                 L.px = tl.px; L.py = tl.py; L.fc = tl.fc; L.rv_max = tl.rv_max;
-                SGX_CUDA(launch_render(L, items[a].nwidth, (int)nheight, tl.smem_bytes, stream_));
+                SGX_CUDA(launch_render(L, items[a].nwidth, (int)nheight, tl.smem_bytes, tl.fast != 0, stream_));
             }
             a = b;
         }
@@ -629,7 +629,7 @@ void stage_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint3
     RenderLaunch L{};
     L.tracks = dr.p; L.n_tracks = 1; L.from_db = 0; L.range = nullptr; L.channels = channels;
     L.px = tl.px; L.py = tl.py; L.fc = tl.fc; L.rv_max = tl.rv_max;
-    SGX_CUDA(launch_render(L, (int)nwidth, (int)nheight, tl.smem_bytes, s));
+    SGX_CUDA(launch_render(L, (int)nwidth, (int)nheight, tl.smem_bytes, tl.fast != 0, s));
     SGX_CUDA(cudaMemcpyAsync(out, dout.p, need, cudaMemcpyDeviceToHost, s));
     SGX_CUDA(cudaStreamSynchronize(s));
 }

@@ -49,10 +49,10 @@ struct AxisTable { int *left, *cnt; float *sum, *w; int taps; int n_in, n_out; b
 uint32_t lanczos3_max_taps(uint32_t n_in, uint32_t n_out);
 cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_major, int *left,
                                     int *cnt, float *sum, float *w, cudaStream_t s);
-struct RenderTiling { int px, py, fc, rv_max; size_t smem_bytes; };
+struct RenderTiling { int px, py, fc, rv_max; size_t smem_bytes; int fast; };
 RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight);
 cudaError_t launch_render(const RenderLaunch &launch, int max_nwidth, int max_nheight,
-                          size_t smem_bytes, cudaStream_t s);
+                          size_t smem_bytes, bool fast, cudaStream_t s);
 
 // small elementwise kernels of the stage API
 cudaError_t launch_spec_to_grey(const float *spec, int n_frames, int n_out, int height, float max_db,

@@ -256,6 +256,113 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaun
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K3 fast path: both axes magnify or keep size (n_in / n_out < 7/6), so every output index has at most
+// 8 Lanczos3 taps.  A CTA renders a 64 x 64 pixel tile:
+//   A  dB -> grey tile G[frame][row] in shared memory (coalesced along bins),
+//   B  vertical pass: lane <-> output row, its 8 (normalised) weights live in registers, the warp walks
+//      the frames of the tile; one shared load per FMA, conflict free (neighbouring rows read
+//      neighbouring words); result clamped at 0 into Tm[row][frame],
+//   C  horizontal pass: lane <-> output column, 8 weights in registers, the warp walks the rows; then
+//      clamp, colour map and one coalesced 128-byte store of 32 RGBA pixels per warp.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFpTile = 64;     // output pixels per tile edge
+constexpr int kFpTaps = 8;
+constexpr int kFpCap = 88;      // source frames / rows a tile can need: 63 * 7/6 + 8 + slack
+constexpr int kFpPitch = 89;    // odd: the transposing accesses of phases B and C stay conflict free
+constexpr size_t kFpSmem = (size_t)(kFpCap * kFpPitch + kFpTile * kFpPitch) * sizeof(float);
+
+__global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const RenderLaunch L)
+{
+    extern __shared__ __align__(16) float rsm[];
+    __shared__ float cm[30];
+    float *G = rsm;                         // [frame][row]
+    float *Tm = rsm + kFpCap * kFpPitch;    // [out row][frame]
+    const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
+    const int nwidth = tr->nwidth, nheight = tr->nheight;
+    const int ox0 = blockIdx.x * kFpTile, oy0 = blockIdx.y * kFpTile;
+    if (ox0 >= nwidth || oy0 >= nheight) return;
+    const int pxc = min(kFpTile, nwidth - ox0), pyc = min(kFpTile, nheight - oy0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 30) cm[tid] = (float)kColormap[tid / 3][tid % 3];
+
+    const int *__restrict__ h_left = tr->h_left;
+    const int *__restrict__ v_left = tr->v_left;
+    const float *__restrict__ src = tr->src;
+    const int width = tr->width, height = tr->height, n_out = tr->n_out;
+
+    const int fl = __ldg(h_left + ox0);
+    const int nfr = min(__ldg(h_left + ox0 + pxc - 1) + kFpTaps - fl, kFpCap);
+    const int yl = __ldg(v_left + oy0);
+    const int nrow = min(__ldg(v_left + oy0 + pyc - 1) + kFpTaps - yl, kFpCap);
+
+    // ---- A: grey tile ------------------------------------------------------------------------------
+    float min_db = 0.0f, inv_span = 0.0f;
+    if (L.from_db) { min_db = L.range[1]; inv_span = __frcp_rn(L.range[0] - L.range[1]); }
+    const int pad_rows = height - n_out; // rows above the spectrogram are 0 (display.rs:47-52)
+    for (int fx = warp; fx < nfr; fx += kRenderThreads / 32) {
+        const int f = fl + fx;
+        const float *__restrict__ col = src + (size_t)f * n_out + (height - 1);
+        for (int yy = lane; yy < nrow; yy += 32) {
+            const int y = yl + yy;
+            float g = 0.0f;
+            if (f < width && y < height) {
+                if (L.from_db) { if (y >= pad_rows) g = __saturatef((__ldg(col - y) - min_db) * inv_span); }
+                else g = __ldg(src + (size_t)y * width + f);
+            }
+            G[fx * kFpPitch + yy] = g;
+        }
+    }
+    __syncthreads();
+
+    // ---- B: vertical pass ----------------------------------------------------------------------------
+    {
+        const int oyl = (warp & 1) * 32 + lane;
+        const int oy = oy0 + min(oyl, pyc - 1);
+        const float *__restrict__ wrow = tr->v_w + (size_t)oy * tr->v_taps;
+        const float sum = __ldg(tr->v_sum + oy);
+        float w[kFpTaps];
+#pragma unroll
+        for (int i = 0; i < kFpTaps; ++i) w[i] = __fdiv_rn(__ldg(wrow + i), sum);
+        const float *g = G + (__ldg(v_left + oy) - yl);
+        float *t_out = Tm + oyl * kFpPitch;
+        if (oyl < pyc) {
+            for (int fx = warp >> 1; fx < nfr; fx += kRenderThreads / 64) {
+                const float *gc = g + fx * kFpPitch;
+                float t = 0.0f;
+#pragma unroll
+                for (int i = 0; i < kFpTaps; ++i) t = fmaf(gc[i], w[i], t);
+                t_out[fx] = clamp_pos(t);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- C: horizontal pass, colour, store -----------------------------------------------------------------
+    {
+        const int oxl = (warp & 1) * 32 + lane;
+        const int ox = ox0 + min(oxl, pxc - 1);
+        const float sum = __ldg(tr->h_sum + ox);
+        float w[kFpTaps];
+#pragma unroll
+        for (int i = 0; i < kFpTaps; ++i) w[i] = __fdiv_rn(__ldg(tr->h_w + (size_t)i * nwidth + ox), sum);
+        const float *t_in = Tm + (__ldg(h_left + ox) - fl);
+        unsigned char *__restrict__ outp = tr->out;
+        if (oxl < pxc) {
+            for (int oyl = warp >> 1; oyl < pyc; oyl += kRenderThreads / 64) {
+                const float *tc = t_in + oyl * kFpPitch;
+                float t = 0.0f;
+#pragma unroll
+                for (int i = 0; i < kFpTaps; ++i) t = fmaf(tc[i], w[i], t);
+                const uchar4 c = grey_to_color(clamp_pos(t), cm);
+                const size_t pix = (size_t)(oy0 + oyl) * nwidth + ox;
+                if (L.channels == 4) reinterpret_cast<uchar4 *>(outp)[pix] = c;
+                else { outp[pix * 3] = c.x; outp[pix * 3 + 1] = c.y; outp[pix * 3 + 2] = c.z; }
+            }
+        }
+    }
+}
+
 // display.rs:44-54 as a stand-alone stage (surface 2)
 __global__ void spec_to_grey_kernel(const float *__restrict__ spec, int T, int n_out, int height,
                                     float max_db, float min_db, float *__restrict__ grey)
@@ -382,6 +489,13 @@ cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_majo
 
 RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
 {
+    // fast path: at most 8 taps per output index on both axes (same f32 ratio the tap tables use)
+    const float rhf = (float)width / (float)nwidth, rvf = (float)height / (float)nheight;
+    if (rhf < 1.16f && rvf < 1.16f) {
+        RenderTiling t{};
+        t.px = kFpTile; t.py = kFpTile; t.fc = kFpCap; t.rv_max = kFpCap; t.smem_bytes = kFpSmem; t.fast = 1;
+        return t;
+    }
     // frames a tile of px output columns needs, rows a tile of py output rows needs
     const double rh = (double)width / nwidth, rv = (double)height / nheight;
     const double sh = 3.0 * (rh < 1 ? 1 : rh), sv = 3.0 * (rv < 1 ? 1 : rv);
@@ -405,22 +519,35 @@ RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
             double cost = halo_h * (1.0 + 0.5 * halo_v);
             if (px * py < kRenderThreads * 4) cost *= 1.0 + (double)(kRenderThreads * 4) / (px * py) * 0.25;
             if (px < 32) cost *= 1.0 + (32.0 / px - 1.0) * 0.5; // sub-line pixel stores
-            if (cost < best_cost) { best_cost = cost; best = RenderTiling{px, py, fc, rvm, smem}; }
+            if (cost < best_cost) { best_cost = cost; best = RenderTiling{px, py, fc, rvm, smem, 0}; }
         }
     }
     if (best.px == 0) { // nothing fits: one pixel per tile, minimum chunk
         const int rvm = rows_for(1);
         int fc = 16;
         while (fc > 1 && ((size_t)fc * (rvm | 1) + (fc + 1)) * sizeof(float) > 200 * 1024) fc >>= 1;
-        best = RenderTiling{1, 1, fc, rvm, ((size_t)fc * (rvm | 1) + (fc + 1)) * sizeof(float)};
+        best = RenderTiling{1, 1, fc, rvm, ((size_t)fc * (rvm | 1) + (fc + 1)) * sizeof(float), 0};
     }
     return best;
 }
 
 cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight, size_t smem_bytes,
-                          cudaStream_t s)
+                          bool fast, cudaStream_t s)
 {
     if (L.n_tracks <= 0 || max_nwidth <= 0 || max_nheight <= 0) return cudaSuccess;
+    if (fast) {
+        static bool fast_configured = false;
+        if (!fast_configured) {
+            cudaError_t e = cudaFuncSetAttribute(render_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kFpSmem);
+            if (e != cudaSuccess) return e;
+            fast_configured = true;
+        }
+        dim3 grid((max_nwidth + kFpTile - 1) / kFpTile, (max_nheight + kFpTile - 1) / kFpTile, L.n_tracks);
+        render_fast_kernel<<<grid, kRenderThreads, kFpSmem, s>>>(L);
+        count_launch();
+        return cudaGetLastError();
+    }
     static size_t configured = 48 * 1024;
     if (smem_bytes > configured) {
         cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

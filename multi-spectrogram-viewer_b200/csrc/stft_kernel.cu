@@ -54,6 +54,14 @@ template <int V> __device__ __forceinline__ void st_vec(float *p, const float (&
     }
 }
 
+// sqrt.approx.f32: max relative error 2^-23 (PTX ISA) -- one MUFU instead of the IEEE sequence
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS) ----------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p)
 {
@@ -140,7 +148,6 @@ __device__ __forceinline__ void dft_inplace(float (&re)[PTS][V], float (&im)[PTS
         float tr[R][V], ti[R][V];
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
-            constexpr int dummy = 0; (void)dummy;
             const int e = BASE + 2 * k * STRIDE, o = BASE + (2 * k + 1) * STRIDE;
             const int widx = k * (16 / R); // exp(-2 pi i k / R) = kC16[widx] - i kS16[widx]
 #pragma unroll
@@ -186,14 +193,28 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
             const int k = (gt + q * NT) & (NS - 1);
+            // w[r] = exp(-2 pi i r k / (NS R)): one table load, the powers by complex products
+            // (at most 3 products deep: error a few ulp, far inside the 1e-4 magnitude tolerance)
+            float2 w[R];
+            w[1] = __ldg(tw + k * (H / (NS * R)));
+            if constexpr (R >= 4) {
+                w[2] = make_float2(w[1].x * w[1].x - w[1].y * w[1].y, 2.0f * w[1].x * w[1].y);
+                w[3] = make_float2(w[2].x * w[1].x - w[2].y * w[1].y, w[2].x * w[1].y + w[2].y * w[1].x);
+            }
+            if constexpr (R >= 8) {
+                w[4] = make_float2(w[2].x * w[2].x - w[2].y * w[2].y, 2.0f * w[2].x * w[2].y);
+                w[5] = make_float2(w[4].x * w[1].x - w[4].y * w[1].y, w[4].x * w[1].y + w[4].y * w[1].x);
+                w[6] = make_float2(w[3].x * w[3].x - w[3].y * w[3].y, 2.0f * w[3].x * w[3].y);
+                w[7] = make_float2(w[4].x * w[3].x - w[4].y * w[3].y, w[4].x * w[3].y + w[4].y * w[3].x);
+            }
+            static_assert(R <= 8, "twiddle powers are written out for radix <= 8");
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                const float2 w = __ldg(tw + (r * k) * (H / (NS * R)));
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const float xr = re[q * R + r][v], xi = im[q * R + r][v];
-                    re[q * R + r][v] = xr * w.x - xi * w.y;
-                    im[q * R + r][v] = xr * w.y + xi * w.x;
+                    re[q * R + r][v] = xr * w[r].x - xi * w[r].y;
+                    im[q * R + r][v] = xr * w[r].y + xi * w[r].x;
                 }
             }
         }
@@ -286,6 +307,7 @@ stft_db_kernel(const StftLaunch L)
     const long long S0 = (long long)t0 * hop - win / 2 - pad_l; // first sample of frame t0 (FFT frame)
     const int off0 = (int)(S0 & 3);
     const long long A0 = S0 - off0; // 16-byte aligned start of the staged tile
+    const bool vec_ok = ((hop | off0) & 1) == 0; // all frames of the tile start on an even float
 
     // ---- stage the PCM tile ------------------------------------------------------------------------
     if (L.staged) {
@@ -317,40 +339,46 @@ stft_db_kernel(const StftLaunch L)
         float re[PTS][V], im[PTS][V];
 
         // ---- first-pass inputs: z[m] = g[2m] + i g[2m+1], g = sample * window ---------------------
+        if (L.staged && vec_ok) {
+            // every frame of the tile starts on an even float: one 64-bit shared load per point
+            const float *fb[V];
 #pragma unroll
-        for (int p = 0; p < PTS; ++p) {
-            const int m = gt + (p % R0) * (H / R0); // NB == 1 in the first pass
-            const int n = 2 * m;
-            const float2 w = __ldg(reinterpret_cast<const float2 *>(win_f + n));
+            for (int v = 0; v < V; ++v) fb[v] = tile + off0 + min(fl0 + v, nfr - 1) * hop + 2 * gt;
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const int fl = min(fl0 + v, nfr - 1);
-                float x0, x1;
-                if (L.staged) {
-                    const int b = off0 + fl * hop + n;
-                    x0 = tile[b]; x1 = tile[b + 1];
-                } else {
-                    const long long i = S0 + (long long)fl * hop + n;
-                    x0 = load_sample(pv, i); x1 = load_sample(pv, i + 1);
+            for (int p = 0; p < PTS; ++p) {
+                const int n = 2 * (gt + p * NT);
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(win_f + n));
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float2 x = *reinterpret_cast<const float2 *>(fb[v] + 2 * p * NT);
+                    re[p][v] = x.x * w.x; im[p][v] = x.y * w.y;
                 }
-                re[p][v] = x0 * w.x; im[p][v] = x1 * w.y;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < PTS; ++p) {
+                const int n = 2 * (gt + p * NT); // NB == 1 in the first pass: point p is element gt + p*H/R0
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(win_f + n));
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int fl = min(fl0 + v, nfr - 1);
+                    float x0, x1;
+                    if (L.staged) {
+                        const int b = off0 + fl * hop + n;
+                        x0 = tile[b]; x1 = tile[b + 1];
+                    } else {
+                        const long long i = S0 + (long long)fl * hop + n;
+                        x0 = load_sample(pv, i); x1 = load_sample(pv, i + 1);
+                    }
+                    re[p][v] = x0 * w.x; im[p][v] = x1 * w.y;
+                }
             }
         }
         run_passes<H, PTS, V, 1>(re, im, sre, sim, gt, L.tw);
 
-        // ---- real-FFT split (realfft.rs:140-157), pairs (k, h-k) --------------------------------------
-        constexpr int NP = PTS / 2;
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            const int k = gt + q * NT;
-            const int kb = (H - k) & (H - 1);
-            ld_vec<V>(sre + padi(k) * V, re[q]);       ld_vec<V>(sim + padi(k) * V, im[q]);
-            ld_vec<V>(sre + padi(kb) * V, re[NP + q]); ld_vec<V>(sim + padi(kb) * V, im[NP + q]);
-        }
-        float cr[V], ci[V];
-        ld_vec<V>(sre + padi(H / 2) * V, cr); ld_vec<V>(sim + padi(H / 2) * V, ci);
-        __syncthreads(); // spectrum is in registers; the buffer is free for magnitudes
-
+        // ---- real-FFT split (realfft.rs:140-157) -------------------------------------------------------
+        // The pair (k, h-k) is read and -- in the mel mode -- overwritten with its two magnitudes by the
+        // same thread, so no barrier is needed between reading the spectrum and storing magnitudes.
         auto emit = [&](int idx, const float (&xr)[V], const float (&xi)[V]) {
             if (mode == MODE_COMPLEX) {
 #pragma unroll
@@ -362,7 +390,7 @@ stft_db_kernel(const StftLaunch L)
             }
             float mg[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) mg[v] = sqrtf(fmaf(xr[v], xr[v], xi[v] * xi[v])); // lib.rs:124
+            for (int v = 0; v < V; ++v) mg[v] = sqrt_approx(fmaf(xr[v], xr[v], xi[v] * xi[v])); // lib.rs:124
             if (mode == MODE_MEL_DB) {
                 st_vec<V>(sre + padi(idx) * V, mg);
             } else {
@@ -380,28 +408,34 @@ stft_db_kernel(const StftLaunch L)
             }
         };
 
+        constexpr int NP = PTS / 2;
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const int k = gt + q * NT;
+            const int kb = (H - k) & (H - 1);
+            float ar[V], ai[V], br[V], bi[V];
+            ld_vec<V>(sre + padi(k) * V, ar);  ld_vec<V>(sim + padi(k) * V, ai);
+            ld_vec<V>(sre + padi(kb) * V, br); ld_vec<V>(sim + padi(kb) * V, bi);
             const float2 cs = __ldg(L.split + k); // (cos, sin)(k pi / h)
             float xr[V], xi[V], yr[V], yi[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float sumr = re[q][v] + re[NP + q][v], difr = re[q][v] - re[NP + q][v];
-                const float sumi = im[q][v] + im[NP + q][v], difi = im[q][v] - im[NP + q][v];
-                xr[v] = 0.5f * ((sumr + cs.x * sumi) - cs.y * difr);
-                xi[v] = 0.5f * ((difi - cs.y * sumi) - cs.x * difr);
-                yr[v] = 0.5f * ((sumr - cs.x * sumi) + cs.y * difr);
-                yi[v] = 0.5f * ((-difi - cs.y * sumi) - cs.x * difr);
+                const float sumr = ar[v] + br[v], difr = ar[v] - br[v];
+                const float sumi = ai[v] + bi[v], difi = ai[v] - bi[v];
+                const float p1 = fmaf(cs.x, sumi, -cs.y * difr);  // c*sumi - s*difr
+                const float p2 = fmaf(cs.y, sumi, cs.x * difr);   // s*sumi + c*difr
+                xr[v] = 0.5f * (sumr + p1); xi[v] = 0.5f * (difi - p2);
+                yr[v] = 0.5f * (sumr - p1); yi[v] = -0.5f * (difi + p2);
             }
             emit(k, xr, xi);
             emit(k == 0 ? H : H - k, yr, yi); // k == 0: the partner output is the Nyquist bin
         }
         if (gt == 0) {
-            float xi[V];
+            float cr[V], ci[V];
+            ld_vec<V>(sre + padi(H / 2) * V, cr); ld_vec<V>(sim + padi(H / 2) * V, ci);
 #pragma unroll
-            for (int v = 0; v < V; ++v) xi[v] = -ci[v];
-            emit(H / 2, cr, xi);
+            for (int v = 0; v < V; ++v) ci[v] = -ci[v];
+            emit(H / 2, cr, ci);
         }
 
         // ---- banded mel projection + dB -----------------------------------------------------------
@@ -441,8 +475,8 @@ stft_db_kernel(const StftLaunch L)
                         }
                 }
             }
-            __syncthreads(); // magnitudes consumed before the next iteration overwrites the buffer
         }
+        __syncthreads(); // spectrum / magnitudes consumed before the next iteration overwrites the buffer
     }
 
     // ---- per-track extrema (lib.rs:197-200) ----------------------------------------------------------
