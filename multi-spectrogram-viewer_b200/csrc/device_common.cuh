@@ -27,7 +27,7 @@ struct StftTrack {
     float *out;            // see StftMode
     int n_out;             // h+1 or n_mel
     // banded mel filterbank (MODE_MEL_DB)
-    const int *mel_lo, *mel_cnt, *mel_off;
+    const int *mel_lo, *mel_cnt, *mel_off; // mel_lo points at packed int4 {lo, cnt, off, 0} per filter
     const float *mel_w;
     int mel_log2p;
     unsigned *range_slot;  // [2] order-preserving encodings of (max, min) dB; may be null

@@ -88,9 +88,9 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
         const int tpg = cfg.generic ? 1 : cfg.h / cfg.pts;
         MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg);
         if (cfg.generic) mb.log2_split = 0;
-        tt.mel_lo.upload(mb.lo.data(), mb.lo.size(), s);
-        tt.mel_cnt.upload(mb.cnt.data(), mb.cnt.size(), s);
-        tt.mel_off.upload(mb.off.data(), mb.off.size(), s);
+        std::vector<int> meta(4 * n_mel, 0); // {lo, cnt, off, 0} per filter: one 16-byte load on the device
+        for (size_t m = 0; m < n_mel; ++m) { meta[4 * m] = mb.lo[m]; meta[4 * m + 1] = mb.cnt[m]; meta[4 * m + 2] = mb.off[m]; }
+        tt.mel_lo.upload(meta.data(), meta.size(), s);
         tt.mel_w.upload(mb.w.data(), mb.w.size(), s);
         tt.mel_log2p = mb.log2_split;
     }

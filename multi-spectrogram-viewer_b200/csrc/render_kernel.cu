@@ -259,32 +259,54 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaun
 // ---------------------------------------------------------------------------------------------------
 // K3 fast path: both axes magnify or keep size (n_in / n_out < 7/6), so every output index has at most
 // 8 Lanczos3 taps.  A CTA renders a 64 x 64 pixel tile:
-//   A  dB -> grey tile G[frame][row] in shared memory (coalesced along bins),
-//   B  vertical pass: lane <-> output row, its 8 (normalised) weights live in registers, the warp walks
-//      the frames of the tile; one shared load per FMA, conflict free (neighbouring rows read
-//      neighbouring words); result clamped at 0 into Tm[row][frame],
-//   C  horizontal pass: lane <-> output column, 8 weights in registers, the warp walks the rows; then
-//      clamp, colour map and one coalesced 128-byte store of 32 RGBA pixels per warp.
+//   A  dB -> grey tile G[row][frame] in shared memory; a warp loads 8 rows x 4 frames per request
+//      (one 32-byte sector per frame) so that the transposing store is bank-conflict free,
+//   B  vertical pass: lane <-> output row with its 8 normalised weights in registers; every 128-bit
+//      shared load brings one source row of FOUR frames, i.e. 4 FMAs per load; clamp at 0 (the per-pass
+//      clamp of image 0.23's resize) into Tm[frame][out row],
+//   C  horizontal pass: lane <-> output column, 8 weights in registers, 128-bit loads bring one source
+//      frame of FOUR output rows; clamp, colour map, and per output row one coalesced 128-byte store
+//      of 32 RGBA pixels per warp.
+// Pitches of 84 and 68 floats (odd multiples of 4) keep the 8 lanes of every 128-bit phase on
+// distinct 16-byte bank groups while neighbouring lanes address neighbouring (or equal) rows.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kFpTile = 64;     // output pixels per tile edge
 constexpr int kFpTaps = 8;
-constexpr int kFpCap = 88;      // source frames / rows a tile can need: 63 * 7/6 + 8 + slack
-constexpr int kFpPitch = 89;    // odd: the transposing accesses of phases B and C stay conflict free
-constexpr size_t kFpSmem = (size_t)(kFpCap * kFpPitch + kFpTile * kFpPitch) * sizeof(float);
+constexpr int kFpCap = 84;      // source frames / rows a tile can need: 63 * 1.16 + 8 = 81.1, rounded to 4
+constexpr int kFpGP = 84;       // pitch of G  [row][frame]
+constexpr int kFpTP = 68;       // pitch of Tm [frame][out row]
+constexpr size_t kFpSmem = (size_t)(kFpCap * kFpGP + kFpCap * kFpTP) * sizeof(float);
+
+// display.rs:24-42 with the colour map stored as (a, b) = (stop i, stop i+1) pairs per channel.
+// round() is floor(v + 0.5): identical to f32::round for v >= 0 except within 2^-25 below 0.5.
+__device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const float2 *cmab)
+{
+    const float position = __fmul_rn(10.0f, x);
+    const float fl = floorf(position);
+    const int idx = min(__float2int_rz(fl), 8);
+    const float ratio = __fsub_rn(position, fl);
+    const float om = __fsub_rn(1.0f, ratio);
+    const float2 r = cmab[idx * 3], g = cmab[idx * 3 + 1], b = cmab[idx * 3 + 2];
+    unsigned cr = __float2uint_rd(__fadd_rn(__fadd_rn(__fmul_rn(ratio, r.y), __fmul_rn(om, r.x)), 0.5f));
+    unsigned cg = __float2uint_rd(__fadd_rn(__fadd_rn(__fmul_rn(ratio, g.y), __fmul_rn(om, g.x)), 0.5f));
+    unsigned cb = __float2uint_rd(__fadd_rn(__fadd_rn(__fmul_rn(ratio, b.y), __fmul_rn(om, b.x)), 0.5f));
+    unsigned px = cr | (cg << 8) | (cb << 16) | 0xff000000u;
+    return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
+}
 
 __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const RenderLaunch L)
 {
     extern __shared__ __align__(16) float rsm[];
-    __shared__ float cm[30];
-    float *G = rsm;                         // [frame][row]
-    float *Tm = rsm + kFpCap * kFpPitch;    // [out row][frame]
+    __shared__ float2 cmab[27];
+    float *G = rsm;                      // [row][frame]
+    float *Tm = rsm + kFpCap * kFpGP;    // [frame][out row]
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
     const int nwidth = tr->nwidth, nheight = tr->nheight;
     const int ox0 = blockIdx.x * kFpTile, oy0 = blockIdx.y * kFpTile;
     if (ox0 >= nwidth || oy0 >= nheight) return;
     const int pxc = min(kFpTile, nwidth - ox0), pyc = min(kFpTile, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 30) cm[tid] = (float)kColormap[tid / 3][tid % 3];
+    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3], (float)kColormap[tid / 3 + 1][tid % 3]);
 
     const int *__restrict__ h_left = tr->h_left;
     const int *__restrict__ v_left = tr->v_left;
@@ -293,6 +315,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
 
     const int fl = __ldg(h_left + ox0);
     const int nfr = min(__ldg(h_left + ox0 + pxc - 1) + kFpTaps - fl, kFpCap);
+    const int nfq = (nfr + 3) >> 2;                 // frame quads
     const int yl = __ldg(v_left + oy0);
     const int nrow = min(__ldg(v_left + oy0 + pyc - 1) + kFpTaps - yl, kFpCap);
 
@@ -300,17 +323,24 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
     float min_db = 0.0f, inv_span = 0.0f;
     if (L.from_db) { min_db = L.range[1]; inv_span = __frcp_rn(L.range[0] - L.range[1]); }
     const int pad_rows = height - n_out; // rows above the spectrogram are 0 (display.rs:47-52)
-    for (int fx = warp; fx < nfr; fx += kRenderThreads / 32) {
-        const int f = fl + fx;
-        const float *__restrict__ col = src + (size_t)f * n_out + (height - 1);
-        for (int yy = lane; yy < nrow; yy += 32) {
-            const int y = yl + yy;
-            float g = 0.0f;
-            if (f < width && y < height) {
-                if (L.from_db) { if (y >= pad_rows) g = __saturatef((__ldg(col - y) - min_db) * inv_span); }
-                else g = __ldg(src + (size_t)y * width + f);
+    {
+        const int fsub = lane & 3, rsub = lane >> 2;
+        for (int fq = warp; fq < nfq; fq += kRenderThreads / 32) {
+            const int fx = fq * 4 + fsub;
+            const int f = fl + fx;
+            const bool fok = f < width;
+            const float *__restrict__ col = src + (size_t)(fok ? f : 0) * n_out + (height - 1);
+#pragma unroll 4
+            for (int r0 = 0; r0 < nrow; r0 += 8) {
+                const int yy = r0 + rsub;
+                const int y = yl + yy;
+                float g = 0.0f;
+                if (fok && y < height) {
+                    if (L.from_db) { if (y >= pad_rows) g = __saturatef((__ldg(col - y) - min_db) * inv_span); }
+                    else g = __ldg(src + (size_t)y * width + f);
+                }
+                if (yy < kFpCap) G[yy * kFpGP + fx] = g;
             }
-            G[fx * kFpPitch + yy] = g;
         }
     }
     __syncthreads();
@@ -320,19 +350,23 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
         const int oyl = (warp & 1) * 32 + lane;
         const int oy = oy0 + min(oyl, pyc - 1);
         const float *__restrict__ wrow = tr->v_w + (size_t)oy * tr->v_taps;
-        const float sum = __ldg(tr->v_sum + oy);
+        const float rs = __frcp_rn(__ldg(tr->v_sum + oy));
         float w[kFpTaps];
 #pragma unroll
-        for (int i = 0; i < kFpTaps; ++i) w[i] = __fdiv_rn(__ldg(wrow + i), sum);
-        const float *g = G + (__ldg(v_left + oy) - yl);
-        float *t_out = Tm + oyl * kFpPitch;
+        for (int i = 0; i < kFpTaps; ++i) w[i] = __ldg(wrow + i) * rs;
+        const float *g = G + (__ldg(v_left + oy) - yl) * kFpGP;
         if (oyl < pyc) {
-            for (int fx = warp >> 1; fx < nfr; fx += kRenderThreads / 64) {
-                const float *gc = g + fx * kFpPitch;
-                float t = 0.0f;
+            for (int fq = warp >> 1; fq < nfq; fq += kRenderThreads / 64) {
+                float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
 #pragma unroll
-                for (int i = 0; i < kFpTaps; ++i) t = fmaf(gc[i], w[i], t);
-                t_out[fx] = clamp_pos(t);
+                for (int i = 0; i < kFpTaps; ++i) {
+                    const float4 v = *reinterpret_cast<const float4 *>(g + i * kFpGP + fq * 4);
+                    t0 = fmaf(v.x, w[i], t0); t1 = fmaf(v.y, w[i], t1);
+                    t2 = fmaf(v.z, w[i], t2); t3 = fmaf(v.w, w[i], t3);
+                }
+                float *t_out = Tm + (fq * 4) * kFpTP + oyl;
+                t_out[0] = clamp_pos(t0); t_out[kFpTP] = clamp_pos(t1);
+                t_out[2 * kFpTP] = clamp_pos(t2); t_out[3 * kFpTP] = clamp_pos(t3);
             }
         }
     }
@@ -342,22 +376,32 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
     {
         const int oxl = (warp & 1) * 32 + lane;
         const int ox = ox0 + min(oxl, pxc - 1);
-        const float sum = __ldg(tr->h_sum + ox);
+        const float rs = __frcp_rn(__ldg(tr->h_sum + ox));
         float w[kFpTaps];
 #pragma unroll
-        for (int i = 0; i < kFpTaps; ++i) w[i] = __fdiv_rn(__ldg(tr->h_w + (size_t)i * nwidth + ox), sum);
-        const float *t_in = Tm + (__ldg(h_left + ox) - fl);
+        for (int i = 0; i < kFpTaps; ++i) w[i] = __ldg(tr->h_w + (size_t)i * nwidth + ox) * rs;
+        const float *t_in = Tm + (__ldg(h_left + ox) - fl) * kFpTP;
         unsigned char *__restrict__ outp = tr->out;
         if (oxl < pxc) {
-            for (int oyl = warp >> 1; oyl < pyc; oyl += kRenderThreads / 64) {
-                const float *tc = t_in + oyl * kFpPitch;
-                float t = 0.0f;
+            const int nrq = (pyc + 3) >> 2;
+            for (int rq = warp >> 1; rq < nrq; rq += kRenderThreads / 64) {
+                float t[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int i = 0; i < kFpTaps; ++i) t = fmaf(tc[i], w[i], t);
-                const uchar4 c = grey_to_color(clamp_pos(t), cm);
-                const size_t pix = (size_t)(oy0 + oyl) * nwidth + ox;
-                if (L.channels == 4) reinterpret_cast<uchar4 *>(outp)[pix] = c;
-                else { outp[pix * 3] = c.x; outp[pix * 3 + 1] = c.y; outp[pix * 3 + 2] = c.z; }
+                for (int i = 0; i < kFpTaps; ++i) {
+                    const float4 v = *reinterpret_cast<const float4 *>(t_in + i * kFpTP + rq * 4);
+                    t[0] = fmaf(v.x, w[i], t[0]); t[1] = fmaf(v.y, w[i], t[1]);
+                    t[2] = fmaf(v.z, w[i], t[2]); t[3] = fmaf(v.w, w[i], t[3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int oyl = rq * 4 + j;
+                    if (oyl < pyc) {
+                        const unsigned c = grey_to_rgba_fast(clamp_pos(t[j]), cmab);
+                        const size_t pix = (size_t)(oy0 + oyl) * nwidth + ox;
+                        if (L.channels == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
+                        else { outp[pix * 3] = (unsigned char)c; outp[pix * 3 + 1] = (unsigned char)(c >> 8); outp[pix * 3 + 2] = (unsigned char)(c >> 16); }
+                    }
+                }
             }
         }
     }

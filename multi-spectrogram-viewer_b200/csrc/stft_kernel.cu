@@ -175,12 +175,23 @@ __device__ __forceinline__ void dft_inplace(float (&re)[PTS][V], float (&im)[PTS
 // Thread `gt` of the group owns butterflies j = gt + q*NT, q < PTS/R.  Inputs of butterfly j are
 // elements j + r*H/R; outputs go to (j - k)*R + k + r*NS with k = j mod NS.  NS == 1 (first pass):
 // the caller has already put the inputs into the registers and no twiddle is needed.
-template <int H, int PTS, int V, int R, int NS>
+// Barrier over one thread group (the groups of a CTA transform different frames and never share data).
+template <int G, int NT> __device__ __forceinline__ void group_sync(int grp)
+{
+    if constexpr (G == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NT) : "memory");
+}
+
+template <int H, int PTS, int V, int G, int R, int NS>
 __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V], float *sre,
-                                         float *sim, int gt, const float2 *__restrict__ tw)
+                                         float *sim, int gt, int grp, const float2 *__restrict__ tw)
 {
     constexpr int NT = H / PTS, NB = PTS / R;
     if constexpr (NS > 1) {
+        // twiddle bases first: the table loads fly while the shared loads and the barrier complete
+        float2 w1[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) w1[q] = __ldg(tw + ((gt + q * NT) & (NS - 1)) * (H / (NS * R)));
 #pragma unroll
         for (int q = 0; q < NB; ++q)
 #pragma unroll
@@ -189,14 +200,13 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
                 ld_vec<V>(sre + src, re[q * R + r]);
                 ld_vec<V>(sim + src, im[q * R + r]);
             }
-        __syncthreads(); // every thread has its inputs: the buffer may be overwritten
+        group_sync<G, NT>(grp); // every thread has its inputs: the buffer may be overwritten
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
-            const int k = (gt + q * NT) & (NS - 1);
             // w[r] = exp(-2 pi i r k / (NS R)): one table load, the powers by complex products
             // (at most 3 products deep: error a few ulp, far inside the 1e-4 magnitude tolerance)
             float2 w[R];
-            w[1] = __ldg(tw + k * (H / (NS * R)));
+            w[1] = w1[q];
             if constexpr (R >= 4) {
                 w[2] = make_float2(w[1].x * w[1].x - w[1].y * w[1].y, 2.0f * w[1].x * w[1].y);
                 w[3] = make_float2(w[2].x * w[1].x - w[2].y * w[1].y, w[2].x * w[1].y + w[2].y * w[1].x);
@@ -243,17 +253,17 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
             st_vec<V>(sim + dst, im[q * R + r]);
         }
     }
-    __syncthreads();
+    group_sync<G, NT>(grp);
 }
 
-template <int H, int PTS, int V, int NS>
+template <int H, int PTS, int V, int G, int NS>
 __device__ __forceinline__ void run_passes(float (&re)[PTS][V], float (&im)[PTS][V], float *sre,
-                                           float *sim, int gt, const float2 *__restrict__ tw)
+                                           float *sim, int gt, int grp, const float2 *__restrict__ tw)
 {
     if constexpr (NS < H) {
         constexpr int R = (H / NS >= PTS) ? PTS : (H / NS);
-        fft_pass<H, PTS, V, R, NS>(re, im, sre, sim, gt, tw);
-        run_passes<H, PTS, V, NS * R>(re, im, sre, sim, gt, tw);
+        fft_pass<H, PTS, V, G, R, NS>(re, im, sre, sim, gt, grp, tw);
+        run_passes<H, PTS, V, G, NS * R>(re, im, sre, sim, gt, grp, tw);
     }
 }
 
@@ -374,7 +384,7 @@ stft_db_kernel(const StftLaunch L)
                 }
             }
         }
-        run_passes<H, PTS, V, 1>(re, im, sre, sim, gt, L.tw);
+        run_passes<H, PTS, V, G, 1>(re, im, sre, sim, gt, grp, L.tw);
 
         // ---- real-FFT split (realfft.rs:140-157) -------------------------------------------------------
         // The pair (k, h-k) is read and -- in the mel mode -- overwritten with its two magnitudes by the
@@ -439,26 +449,32 @@ stft_db_kernel(const StftLaunch L)
         }
 
         // ---- banded mel projection + dB -----------------------------------------------------------
+        // Work item = (filter m, lane pl of the 2^lg lanes sharing it); the tap loop runs to the warp's
+        // longest band with predicated loads so that it can be unrolled and the loads overlap.
         if (mode == MODE_MEL_DB) {
-            __syncthreads();
+            group_sync<G, NT>(grp);
             const int lg = td->mel_log2p, P = 1 << lg;
             const int items = n_out << lg;
-            const int *__restrict__ mlo = td->mel_lo; const int *__restrict__ mcnt = td->mel_cnt;
-            const int *__restrict__ moff = td->mel_off; const float *__restrict__ mw = td->mel_w;
+            const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo); // {lo, cnt, off, 0}
+            const float *__restrict__ mw = td->mel_w;
             for (int w0 = 0; w0 < items; w0 += NT) {
                 const int wi = w0 + gt;
                 const int m = wi >> lg, pl = wi & (P - 1);
                 const bool valid = m < n_out;
-                const int blo = valid ? __ldg(mlo + m) : 0;
-                const int bcnt = valid ? __ldg(mcnt + m) : 0;
-                const int boff = valid ? __ldg(moff + m) : 0;
+                const int4 mt = valid ? __ldg(meta + m) : make_int4(0, 0, 0, 0);
+                const int nj = mt.y > pl ? (mt.y - pl + P - 1) >> lg : 0; // taps of this lane: pl, pl+P, ...
+                const int njmax = __reduce_max_sync(0xffffffffu, nj);
+                const float *__restrict__ wp = mw + mt.z + pl;
+                const int bin0 = mt.x + pl;
                 float acc[V];
 #pragma unroll
                 for (int v = 0; v < V; ++v) acc[v] = 0.0f;
-                for (int i = pl; i < bcnt; i += P) {
-                    const float wgt = __ldg(mw + boff + i);
+#pragma unroll 4
+                for (int j = 0; j < njmax; ++j) {
+                    const bool on = j < nj;
+                    const float wgt = on ? __ldg(wp + (j << lg)) : 0.0f;
                     float mg[V];
-                    ld_vec<V>(sre + padi(blo + i) * V, mg);
+                    ld_vec<V>(sre + padi(on ? bin0 + (j << lg) : 0) * V, mg);
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v] = fmaf(mg[v], wgt, acc[v]);
                 }
@@ -476,7 +492,7 @@ stft_db_kernel(const StftLaunch L)
                 }
             }
         }
-        __syncthreads(); // spectrum / magnitudes consumed before the next iteration overwrites the buffer
+        group_sync<G, NT>(grp); // spectrum / magnitudes consumed before the next iteration overwrites the buffer
     }
 
     // ---- per-track extrema (lib.rs:197-200) ----------------------------------------------------------
@@ -567,7 +583,8 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, i
     if (mode == MODE_MEL_DB) {
         __syncthreads();
         for (int m = tid; m < n_out; m += blockDim.x) {
-            const int blo = td->mel_lo[m], bcnt = td->mel_cnt[m], boff = td->mel_off[m];
+            const int4 mt = reinterpret_cast<const int4 *>(td->mel_lo)[m];
+            const int blo = mt.x, bcnt = mt.y, boff = mt.z;
             float acc = 0.0f;
             for (int i = 0; i < bcnt; ++i) acc = fmaf(mag[blo + i], td->mel_w[boff + i], acc);
             const float y = amp_to_db_dev(acc);

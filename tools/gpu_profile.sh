@@ -8,6 +8,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-fil
 echo "ncu launches exit $?"
 ncu --set full --clock-control none --import-source on -k regex:stft_db -s 1 -c 1 -f -o gpurun_out/prof_k1 $CMD > gpurun_out/ncu_k1.log 2>&1
 echo "ncu k1 exit $?"
-ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 1 -c 1 -f -o gpurun_out/prof_k3 $CMD > gpurun_out/ncu_k3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:render_fast -s 1 -c 1 -f -o gpurun_out/prof_k3 $CMD > gpurun_out/ncu_k3.log 2>&1
 echo "ncu k3 exit $?"
 ls -la gpurun_out
