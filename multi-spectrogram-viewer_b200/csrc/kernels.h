@@ -16,6 +16,7 @@ struct StftConfig {
     int vec;               // frames processed together by one thread group (V)
     int groups;            // thread groups per CTA (G)
     int threads;           // G * h / pts
+    int min_ctas;          // resident CTAs per SM the kernel is compiled for
     size_t fft_smem;       // bytes of FFT exchange buffers
     bool generic;          // small-F fallback kernel (one CTA per frame)
 };

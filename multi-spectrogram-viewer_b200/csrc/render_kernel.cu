@@ -319,27 +319,47 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
     const int yl = __ldg(v_left + oy0);
     const int nrow = min(__ldg(v_left + oy0 + pyc - 1) + kFpTaps - yl, kFpCap);
 
+    // weights of phases B and C first: their global loads complete while phase A runs
+    const int oyl_b = (warp & 1) * 32 + lane;
+    const int oy_b = oy0 + min(oyl_b, pyc - 1);
+    const int oxl_c = (warp & 1) * 32 + lane;
+    const int ox_c = ox0 + min(oxl_c, pxc - 1);
+    float wv[kFpTaps], wh[kFpTaps];
+    {
+        const float *__restrict__ wrow = tr->v_w + (size_t)oy_b * tr->v_taps;
+#pragma unroll
+        for (int i = 0; i < kFpTaps; ++i) { wv[i] = __ldg(wrow + i); wh[i] = __ldg(tr->h_w + (size_t)i * nwidth + ox_c); }
+    }
+    const float vsum = __ldg(tr->v_sum + oy_b), hsum = __ldg(tr->h_sum + ox_c);
+    const int voff = __ldg(v_left + oy_b) - yl, hoff = __ldg(h_left + ox_c) - fl;
+
     // ---- A: grey tile ------------------------------------------------------------------------------
     float min_db = 0.0f, inv_span = 0.0f;
     if (L.from_db) { min_db = L.range[1]; inv_span = __frcp_rn(L.range[0] - L.range[1]); }
     const int pad_rows = height - n_out; // rows above the spectrogram are 0 (display.rs:47-52)
     {
         const int fsub = lane & 3, rsub = lane >> 2;
+        constexpr int kRowBatches = (kFpCap + 7) / 8;
         for (int fq = warp; fq < nfq; fq += kRenderThreads / 32) {
             const int fx = fq * 4 + fsub;
             const int f = fl + fx;
             const bool fok = f < width;
             const float *__restrict__ col = src + (size_t)(fok ? f : 0) * n_out + (height - 1);
-#pragma unroll 4
-            for (int r0 = 0; r0 < nrow; r0 += 8) {
-                const int yy = r0 + rsub;
+            // all loads of this frame quad are issued before the first use (memory-level parallelism)
+            float v[kRowBatches];
+#pragma unroll
+            for (int j = 0; j < kRowBatches; ++j) {
+                const int yy = j * 8 + rsub;
                 const int y = yl + yy;
-                float g = 0.0f;
-                if (fok && y < height) {
-                    if (L.from_db) { if (y >= pad_rows) g = __saturatef((__ldg(col - y) - min_db) * inv_span); }
-                    else g = __ldg(src + (size_t)y * width + f);
-                }
-                if (yy < kFpCap) G[yy * kFpGP + fx] = g;
+                const bool ok = fok && yy < nrow && y < height && (!L.from_db || y >= pad_rows);
+                v[j] = L.from_db ? -INFINITY : 0.0f; // -inf -> grey 0 after the saturate
+                if (ok) v[j] = L.from_db ? __ldg(col - y) : __ldg(src + (size_t)y * width + f);
+            }
+#pragma unroll
+            for (int j = 0; j < kRowBatches; ++j) {
+                const int yy = j * 8 + rsub;
+                const float g = L.from_db ? __saturatef((v[j] - min_db) * inv_span) : v[j];
+                if (yy < kFpCap && j * 8 < nrow) G[yy * kFpGP + fx] = g;
             }
         }
     }
@@ -347,14 +367,12 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
 
     // ---- B: vertical pass ----------------------------------------------------------------------------
     {
-        const int oyl = (warp & 1) * 32 + lane;
-        const int oy = oy0 + min(oyl, pyc - 1);
-        const float *__restrict__ wrow = tr->v_w + (size_t)oy * tr->v_taps;
-        const float rs = __frcp_rn(__ldg(tr->v_sum + oy));
+        const int oyl = oyl_b;
+        const float rs = __frcp_rn(vsum);
         float w[kFpTaps];
 #pragma unroll
-        for (int i = 0; i < kFpTaps; ++i) w[i] = __ldg(wrow + i) * rs;
-        const float *g = G + (__ldg(v_left + oy) - yl) * kFpGP;
+        for (int i = 0; i < kFpTaps; ++i) w[i] = wv[i] * rs;
+        const float *g = G + voff * kFpGP;
         if (oyl < pyc) {
             for (int fq = warp >> 1; fq < nfq; fq += kRenderThreads / 64) {
                 float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
@@ -374,13 +392,12 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
 
     // ---- C: horizontal pass, colour, store -----------------------------------------------------------------
     {
-        const int oxl = (warp & 1) * 32 + lane;
-        const int ox = ox0 + min(oxl, pxc - 1);
-        const float rs = __frcp_rn(__ldg(tr->h_sum + ox));
+        const int oxl = oxl_c, ox = ox_c;
+        const float rs = __frcp_rn(hsum);
         float w[kFpTaps];
 #pragma unroll
-        for (int i = 0; i < kFpTaps; ++i) w[i] = __ldg(tr->h_w + (size_t)i * nwidth + ox) * rs;
-        const float *t_in = Tm + (__ldg(h_left + ox) - fl) * kFpTP;
+        for (int i = 0; i < kFpTaps; ++i) w[i] = wh[i] * rs;
+        const float *t_in = Tm + hoff * kFpTP;
         unsigned char *__restrict__ outp = tr->out;
         if (oxl < pxc) {
             const int nrq = (pyc + 3) >> 2;

@@ -21,6 +21,7 @@
 //     coalesced stores, per-thread extrema are reduced to two atomics per CTA.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -192,11 +193,14 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
         float2 w1[NB];
 #pragma unroll
         for (int q = 0; q < NB; ++q) w1[q] = __ldg(tw + ((gt + q * NT) & (NS - 1)) * (H / (NS * R)));
+        // element gt + q*NT + r*H/R: the offsets are multiples of 8, so pad() is linear in them
+        static_assert(NT % 8 == 0 && (H / R) % 8 == 0, "padded addressing assumes multiples of 8");
+        const int sbase = padi(gt) * V;
 #pragma unroll
         for (int q = 0; q < NB; ++q)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int src = padi(gt + q * NT + r * (H / R)) * V;
+                const int src = sbase + ((q * NT + r * (H / R)) / 8 * 9) * V;
                 ld_vec<V>(sre + src, re[q * R + r]);
                 ld_vec<V>(sim + src, im[q * R + r]);
             }
@@ -241,49 +245,82 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
         dft_inplace<R, 4 * R, 1, PTS, V>(re, im); dft_inplace<R, 5 * R, 1, PTS, V>(re, im);
         dft_inplace<R, 6 * R, 1, PTS, V>(re, im); dft_inplace<R, 7 * R, 1, PTS, V>(re, im);
     }
+    if constexpr (NS == 1 && R == 8) {
+        // d = 8 j, element 8 j + r -> padded 9 j + r
 #pragma unroll
-    for (int q = 0; q < NB; ++q) {
-        const int j = gt + q * NT;
-        const int k = j & (NS - 1);
-        const int d = (j - k) * R + k;
+        for (int q = 0; q < NB; ++q)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int dst = padi(d + r * NS) * V;
-            st_vec<V>(sre + dst, re[q * R + r]);
-            st_vec<V>(sim + dst, im[q * R + r]);
+            for (int r = 0; r < R; ++r) {
+                const int dst = (9 * gt + 9 * q * NT + r) * V;
+                st_vec<V>(sre + dst, re[q * R + r]);
+                st_vec<V>(sim + dst, im[q * R + r]);
+            }
+    } else if constexpr (NS % 8 == 0) {
+        // k = j mod NS is the same for every q when NS divides NT; when NS > NT, j < NS and d = j.
+        // All per-(q, r) displacements are multiples of 8: one pad() per pass.
+        constexpr bool kSmall = NS <= NT;
+        const int k = kSmall ? (gt & (NS - 1)) : gt;
+        const int dbase = padi(kSmall ? (gt - k) * R + k : gt) * V;
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int dst = dbase + (((kSmall ? q * NT * R : q * NT) + r * NS) / 8 * 9) * V;
+                st_vec<V>(sre + dst, re[q * R + r]);
+                st_vec<V>(sim + dst, im[q * R + r]);
+            }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int j = gt + q * NT;
+            const int k = j & (NS - 1);
+            const int d = (j - k) * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int dst = padi(d + r * NS) * V;
+                st_vec<V>(sre + dst, re[q * R + r]);
+                st_vec<V>(sim + dst, im[q * R + r]);
+            }
         }
     }
     group_sync<G, NT>(grp);
 }
 
-template <int H, int PTS, int V, int G, int NS>
+// Runs the passes whose input stride product NS is below NS_END (H: all passes).
+template <int H, int PTS, int V, int G, int NS, int NS_END>
 __device__ __forceinline__ void run_passes(float (&re)[PTS][V], float (&im)[PTS][V], float *sre,
                                            float *sim, int gt, int grp, const float2 *__restrict__ tw)
 {
-    if constexpr (NS < H) {
+    if constexpr (NS < NS_END) {
         constexpr int R = (H / NS >= PTS) ? PTS : (H / NS);
         fft_pass<H, PTS, V, G, R, NS>(re, im, sre, sim, gt, grp, tw);
-        run_passes<H, PTS, V, G, NS * R>(re, im, sre, sim, gt, grp, tw);
+        run_passes<H, PTS, V, G, NS * R, NS_END>(re, im, sre, sim, gt, grp, tw);
     }
 }
 
-template <int LOG2H, int PTS, int V, int G> struct K1Traits {
+// radix of the last pass of the schedule above
+__host__ __device__ constexpr int last_radix(int h, int pts)
+{
+    int n = h;
+    while (n >= pts) n /= pts;
+    return n > 1 ? n : pts;
+}
+
+template <int LOG2H, int PTS, int V, int G, int MC> struct K1Traits {
     static constexpr int H = 1 << LOG2H;
     static constexpr int NT = H / PTS;
     static constexpr int THREADS = G * NT;
     static constexpr int PADH = ((H + (H >> 3) + 1) + 3) & ~3; // elements of V floats
     static constexpr size_t FFT_SMEM = (size_t)G * 2 * PADH * V * sizeof(float);
-    static constexpr int MIN_CTAS = THREADS <= 256 ? 2 : 1;
+    static constexpr int MIN_CTAS = MC; // resident CTAs per SM the register budget is shaped for
 };
 
-template <int LOG2H, int PTS, int V, int G>
-__global__ void __launch_bounds__(K1Traits<LOG2H, PTS, V, G>::THREADS,
-                                  K1Traits<LOG2H, PTS, V, G>::MIN_CTAS)
+template <int LOG2H, int PTS, int V, int G, int MC>
+__global__ void __launch_bounds__(K1Traits<LOG2H, PTS, V, G, MC>::THREADS, MC)
 stft_db_kernel(const StftLaunch L)
 {
-    using TR = K1Traits<LOG2H, PTS, V, G>;
+    using TR = K1Traits<LOG2H, PTS, V, G, MC>;
     constexpr int H = TR::H, NT = TR::NT, THREADS = TR::THREADS, PADH = TR::PADH, F = 2 * H;
-    constexpr int R0 = PTS; // H >= PTS always for this kernel
     static_assert(NT >= 32 && (NT % 32) == 0, "a group must be whole warps");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -384,12 +421,10 @@ stft_db_kernel(const StftLaunch L)
                 }
             }
         }
-        run_passes<H, PTS, V, G, 1>(re, im, sre, sim, gt, grp, L.tw);
-
         // ---- real-FFT split (realfft.rs:140-157) -------------------------------------------------------
-        // The pair (k, h-k) is read and -- in the mel mode -- overwritten with its two magnitudes by the
-        // same thread, so no barrier is needed between reading the spectrum and storing magnitudes.
-        auto emit = [&](int idx, const float (&xr)[V], const float (&xi)[V]) {
+        // emit(): what becomes of one output bin -- complex / magnitude / dB to HBM, or (mel) its
+        // magnitude into the shared buffer at the bin's own (padded) position.
+        auto emit = [&](int idx, int spos, const float (&xr)[V], const float (&xi)[V]) {
             if (mode == MODE_COMPLEX) {
 #pragma unroll
                 for (int v = 0; v < V; ++v)
@@ -402,7 +437,7 @@ stft_db_kernel(const StftLaunch L)
 #pragma unroll
             for (int v = 0; v < V; ++v) mg[v] = sqrt_approx(fmaf(xr[v], xr[v], xi[v] * xi[v])); // lib.rs:124
             if (mode == MODE_MEL_DB) {
-                st_vec<V>(sre + padi(idx) * V, mg);
+                st_vec<V>(sre + spos, mg);
             } else {
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
@@ -418,14 +453,9 @@ stft_db_kernel(const StftLaunch L)
             }
         };
 
-        constexpr int NP = PTS / 2;
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            const int k = gt + q * NT;
-            const int kb = (H - k) & (H - 1);
-            float ar[V], ai[V], br[V], bi[V];
-            ld_vec<V>(sre + padi(k) * V, ar);  ld_vec<V>(sim + padi(k) * V, ai);
-            ld_vec<V>(sre + padi(kb) * V, br); ld_vec<V>(sim + padi(kb) * V, bi);
+        // one conjugate-symmetric pair: a = Z[k], b = Z[h-k], k <= h/2 -> X[k] and (optionally) X[h-k]
+        auto split_pair = [&](int k, const float (&ar)[V], const float (&ai)[V], const float (&br)[V],
+                              const float (&bi)[V], bool emit_partner) {
             const float2 cs = __ldg(L.split + k); // (cos, sin)(k pi / h)
             float xr[V], xi[V], yr[V], yi[V];
 #pragma unroll
@@ -437,16 +467,121 @@ stft_db_kernel(const StftLaunch L)
                 xr[v] = 0.5f * (sumr + p1); xi[v] = 0.5f * (difi - p2);
                 yr[v] = 0.5f * (sumr - p1); yi[v] = -0.5f * (difi + p2);
             }
-            emit(k, xr, xi);
-            emit(k == 0 ? H : H - k, yr, yi); // k == 0: the partner output is the Nyquist bin
+            emit(k, padi(k) * V, xr, xi);
+            if (emit_partner) { const int kp = k == 0 ? H : H - k; emit(kp, padi(kp) * V, yr, yi); } // k == 0: Nyquist bin
+        };
+
+        constexpr int RL = last_radix(H, PTS);
+        constexpr bool FUSED = (PTS / RL) >= 2;
+        if constexpr (FUSED) {
+            // ---- last pass fused with the split ---------------------------------------------------------
+            // Butterfly j of the last pass (radix RL, NSL = H/RL) produces Z[j + r NSL]; the conjugate
+            // partner of that bin comes out of butterfly NSL - j.  Each thread therefore runs butterfly
+            // PAIRS (j, NSL - j): the spectrum never returns to shared memory and the split costs no loads.
+            run_passes<H, PTS, V, G, 1, H / RL>(re, im, sre, sim, gt, grp, L.tw);
+            constexpr int NSL = H / RL, NPR = (PTS / RL) / 2;
+            static_assert(NSL % 8 == 0, "padded addressing assumes multiples of 8");
+            int bA[NPR], bB[NPR];
+            float2 wA[NPR], wB[NPR];
+#pragma unroll
+            for (int p = 0; p < NPR; ++p) {
+                bA[p] = gt + p * NT;                                          // in [0, NSL/2)
+                bB[p] = (p == 0 && gt == 0) ? NSL / 2 : NSL - bA[p];          // thread 0 also owns NSL/2
+                wA[p] = __ldg(L.tw + bA[p]); wB[p] = __ldg(L.tw + bB[p]);     // exp(-2 pi i j / H)
+            }
+#pragma unroll
+            for (int p = 0; p < NPR; ++p) {
+                const int sa = padi(bA[p]) * V, sb = padi(bB[p]) * V;
+#pragma unroll
+                for (int r = 0; r < RL; ++r) {
+                    ld_vec<V>(sre + sa + (r * NSL / 8 * 9) * V, re[(2 * p) * RL + r]);
+                    ld_vec<V>(sim + sa + (r * NSL / 8 * 9) * V, im[(2 * p) * RL + r]);
+                    ld_vec<V>(sre + sb + (r * NSL / 8 * 9) * V, re[(2 * p + 1) * RL + r]);
+                    ld_vec<V>(sim + sb + (r * NSL / 8 * 9) * V, im[(2 * p + 1) * RL + r]);
+                }
+            }
+            if (mode == MODE_MEL_DB) group_sync<G, NT>(grp); // the buffer now becomes the magnitude array
+#pragma unroll
+            for (int b = 0; b < 2 * NPR; ++b) {
+                float2 w[RL];
+                w[1] = (b & 1) ? wB[b >> 1] : wA[b >> 1];
+                if constexpr (RL >= 4) {
+                    w[2] = make_float2(w[1].x * w[1].x - w[1].y * w[1].y, 2.0f * w[1].x * w[1].y);
+                    w[3] = make_float2(w[2].x * w[1].x - w[2].y * w[1].y, w[2].x * w[1].y + w[2].y * w[1].x);
+                }
+                static_assert(RL <= 4, "fused last pass is written for radix 2 and 4");
+#pragma unroll
+                for (int r = 1; r < RL; ++r)
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const float xr = re[b * RL + r][v], xi = im[b * RL + r][v];
+                        re[b * RL + r][v] = xr * w[r].x - xi * w[r].y;
+                        im[b * RL + r][v] = xr * w[r].y + xi * w[r].x;
+                    }
+            }
+            if constexpr (NPR >= 1) { dft_inplace<RL, 0, 1, PTS, V>(re, im); dft_inplace<RL, RL, 1, PTS, V>(re, im); }
+            if constexpr (NPR >= 2) { dft_inplace<RL, 2 * RL, 1, PTS, V>(re, im); dft_inplace<RL, 3 * RL, 1, PTS, V>(re, im); }
+            if constexpr (NPR >= 3) { dft_inplace<RL, 4 * RL, 1, PTS, V>(re, im); dft_inplace<RL, 5 * RL, 1, PTS, V>(re, im); }
+            if constexpr (NPR >= 4) { dft_inplace<RL, 6 * RL, 1, PTS, V>(re, im); dft_inplace<RL, 7 * RL, 1, PTS, V>(re, im); }
+            static_assert(NPR <= 4, "unsupported butterfly pairs per thread");
+#pragma unroll
+            for (int p = 0; p < NPR; ++p) {
+                const int ba = (2 * p) * RL, bb = (2 * p + 1) * RL; // register blocks of butterflies bA, bB
+                if (p == 0 && gt == 0) {
+                    // butterfly 0 pairs with itself: Z[r NSL] <-> Z[(RL - r) NSL]; r = 0 and r = RL/2 are self-conjugate
+                    split_pair(0, re[ba], im[ba], re[ba], im[ba], true);
+#pragma unroll
+                    for (int r = 1; r < RL / 2; ++r)
+                        split_pair(r * NSL, re[ba + r], im[ba + r], re[ba + RL - r], im[ba + RL - r], true);
+                    split_pair(H / 2, re[ba + RL / 2], im[ba + RL / 2], re[ba + RL / 2], im[ba + RL / 2], false);
+                    // butterfly NSL/2 pairs with itself: Z[NSL/2 + r NSL] <-> Z[NSL/2 + (RL-1-r) NSL]
+#pragma unroll
+                    for (int r = 0; r < RL / 2; ++r)
+                        split_pair(NSL / 2 + r * NSL, re[bb + r], im[bb + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RL / 2; ++r) {
+                        split_pair(bA[p] + r * NSL, re[ba + r], im[ba + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
+                        split_pair(bB[p] + r * NSL, re[bb + r], im[bb + r], re[ba + RL - 1 - r], im[ba + RL - 1 - r], true);
+                    }
+                }
+            }
+        } else {
+        run_passes<H, PTS, V, G, 1, H>(re, im, sre, sim, gt, grp, L.tw);
+        constexpr int NP = PTS / 2;
+        const int pa0 = padi(gt) * V;      // element k = gt + q NT      -> pa0 + 9 q NT / 8
+        const int pb0 = padi(H - gt) * V;  // element H - k (k > 0)      -> pb0 - 9 q NT / 8
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int k = gt + q * NT;
+            const int pa = pa0 + (q * NT / 8 * 9) * V;
+            const int pbm = pb0 - (q * NT / 8 * 9) * V;     // where the partner's magnitude goes (index H when k == 0)
+            const int pb = (q == 0 && gt == 0) ? 0 : pbm;   // where the partner's spectrum is read (index 0 when k == 0)
+            float ar[V], ai[V], br[V], bi[V];
+            ld_vec<V>(sre + pa, ar); ld_vec<V>(sim + pa, ai);
+            ld_vec<V>(sre + pb, br); ld_vec<V>(sim + pb, bi);
+            const float2 cs = __ldg(L.split + k); // (cos, sin)(k pi / h)
+            float xr[V], xi[V], yr[V], yi[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float sumr = ar[v] + br[v], difr = ar[v] - br[v];
+                const float sumi = ai[v] + bi[v], difi = ai[v] - bi[v];
+                const float p1 = fmaf(cs.x, sumi, -cs.y * difr);  // c*sumi - s*difr
+                const float p2 = fmaf(cs.y, sumi, cs.x * difr);   // s*sumi + c*difr
+                xr[v] = 0.5f * (sumr + p1); xi[v] = 0.5f * (difi - p2);
+                yr[v] = 0.5f * (sumr - p1); yi[v] = -0.5f * (difi + p2);
+            }
+            emit(k, pa, xr, xi);
+            emit(k == 0 ? H : H - k, pbm, yr, yi); // k == 0: the partner output is the Nyquist bin
         }
         if (gt == 0) {
             float cr[V], ci[V];
             ld_vec<V>(sre + padi(H / 2) * V, cr); ld_vec<V>(sim + padi(H / 2) * V, ci);
 #pragma unroll
             for (int v = 0; v < V; ++v) ci[v] = -ci[v];
-            emit(H / 2, cr, ci);
+            emit(H / 2, padi(H / 2) * V, cr, ci);
         }
+        } // !FUSED
 
         // ---- banded mel projection + dB -----------------------------------------------------------
         // Work item = (filter m, lane pl of the 2^lg lanes sharing it); the tap loop runs to the warp's
@@ -611,11 +746,11 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, i
     }
 }
 
-template <int LOG2H, int PTS, int V, int G>
+template <int LOG2H, int PTS, int V, int G, int MC>
 cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
-    using TR = K1Traits<LOG2H, PTS, V, G>;
-    auto kern = stft_db_kernel<LOG2H, PTS, V, G>;
+    using TR = K1Traits<LOG2H, PTS, V, G, MC>;
+    auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC>;
     static size_t configured = 0; // per instantiation
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -629,27 +764,44 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 
 } // namespace
 
-// FFT size -> kernel instantiation
+// FFT size -> kernel instantiations (LOG2H, PTS, V, G).  The first entry of a size is the default; the
+// others are selectable with SGX_K1_VARIANT="pts,v,g" (tuning experiments).
 #define SGX_K1_TABLE(X) \
-    X(8, 8, 4, 8)       \
-    X(9, 8, 4, 4)       \
-    X(10, 8, 4, 2)      \
-    X(11, 8, 4, 1)      \
-    X(12, 8, 4, 1)      \
-    X(13, 8, 2, 1)
+    X(8, 8, 4, 8, 2)    \
+    X(9, 8, 4, 4, 2)    \
+    X(10, 8, 4, 2, 2)   \
+    X(10, 8, 2, 2, 3)   \
+    X(10, 8, 2, 4, 2)   \
+    X(10, 4, 4, 1, 4)   \
+    X(10, 4, 4, 2, 2)   \
+    X(11, 8, 4, 1, 2)   \
+    X(11, 8, 2, 1, 3)   \
+    X(11, 8, 2, 2, 1)   \
+    X(12, 8, 4, 1, 1)   \
+    X(12, 8, 2, 1, 1)   \
+    X(13, 8, 2, 1, 1)
 
 bool stft_config_for(size_t n_fft, StftConfig *cfg)
 {
     if (n_fft < 2 || (n_fft & (n_fft - 1)) != 0 || n_fft > 16384) return false;
     const int h = (int)(n_fft / 2);
     cfg->n_fft = (int)n_fft; cfg->h = h; cfg->generic = true;
-    cfg->pts = 2; cfg->vec = 1; cfg->groups = 1; cfg->threads = 128;
+    cfg->pts = 2; cfg->vec = 1; cfg->groups = 1; cfg->threads = 128; cfg->min_ctas = 1;
     cfg->fft_smem = (size_t)(2 * h) * sizeof(float2) + (size_t)(h + 1) * sizeof(float);
-#define X(LG, PTS, V, G)                                              \
-    if (h == (1 << LG)) {                                             \
-        using TR = K1Traits<LG, PTS, V, G>;                           \
-        cfg->generic = false; cfg->pts = PTS; cfg->vec = V; cfg->groups = G; \
-        cfg->threads = TR::THREADS; cfg->fft_smem = TR::FFT_SMEM;     \
+    int want_pts = 0, want_v = 0, want_g = 0;
+    if (const char *e = getenv("SGX_K1_VARIANT")) sscanf(e, "%d,%d,%d", &want_pts, &want_v, &want_g);
+    bool chosen = false;
+#define X(LG, PTS, V, G, MC)                                                                     \
+    if (h == (1 << LG)) {                                                                        \
+        using TR = K1Traits<LG, PTS, V, G, MC>;                                                      \
+        const bool match = want_pts == PTS && want_v == V && want_g == G;                        \
+        if (!chosen || match) {                                                                  \
+            if (cfg->generic || match) {                                                         \
+                cfg->generic = false; cfg->pts = PTS; cfg->vec = V; cfg->groups = G;             \
+                cfg->threads = TR::THREADS; cfg->fft_smem = TR::FFT_SMEM; cfg->min_ctas = TR::MIN_CTAS; \
+            }                                                                                    \
+            chosen = chosen || match;                                                            \
+        }                                                                                        \
     }
     SGX_K1_TABLE(X)
 #undef X
@@ -667,21 +819,25 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop)
         return t;
     }
     const int unit = cfg.groups * cfg.vec;
-    // target two resident CTAs per SM for <= 256-thread CTAs, one otherwise
-    const size_t budget = (cfg.threads <= 256 ? (size_t)113 * 1024 : stft_max_dynamic_smem()) - 1024;
+    // per-CTA shared-memory budget for the register-limited number of resident CTAs (228 KB per SM,
+    // 1 KB reserved per CTA); the staged tile gets what the FFT buffers leave
+    const int ctas = cfg.min_ctas > 0 ? cfg.min_ctas : 1;
+    size_t budget = (size_t)(228 * 1024) / ctas - 1024 - 512;
+    if (budget > stft_max_dynamic_smem()) budget = stft_max_dynamic_smem();
     const size_t avail = budget > cfg.fft_smem + 16 ? budget - cfg.fft_smem - 16 : 0;
     const long cap_floats = (long)(avail / sizeof(float));
+    int want_nfr = 0;
+    if (const char *e = getenv("SGX_K1_NFR")) want_nfr = atoi(e);
     // floats(nfr) = 3 + (nfr-1)*hop + F, rounded up to 4
     int best = 0;
     for (int mult = 1; mult <= 8; ++mult) {
         const int nfr = unit * mult;
         const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
-        if (need <= cap_floats) best = nfr;
+        if (need <= cap_floats && (want_nfr == 0 || nfr <= want_nfr || best == 0)) best = nfr;
     }
     if (best == 0) {
         t.frames_per_tile = unit; t.staged = 0; t.tile_floats = 0;
     } else {
-        // prefer >= 16 frames (amortises the halo) but do not shrink what fits
         t.frames_per_tile = best; t.staged = 1;
         long need = 3 + (long)(best - 1) * max_hop + cfg.n_fft;
         t.tile_floats = (int)((need + 3) & ~3L) + 4;
@@ -720,8 +876,8 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t
         count_launch();
         return cudaGetLastError();
     }
-#define X(LG, PTS, V, G) \
-    if (cfg.h == (1 << LG)) return launch_one<LG, PTS, V, G>(L, smem, stream);
+#define X(LG, PTS, V, G, MC) \
+    if (cfg.h == (1 << LG) && cfg.pts == PTS && cfg.vec == V && cfg.groups == G) return launch_one<LG, PTS, V, G, MC>(L, smem, stream);
     SGX_K1_TABLE(X)
 #undef X
     return cudaErrorInvalidValue;
