@@ -133,6 +133,7 @@ def run_cpu(wl, steps, warmup):
     import msv_b200 as msv
 
     orc = oracle_binding.load()
+    orc.set_num_threads(len(os.sched_getaffinity(0)))  # all host cores (torchrun pins OMP_NUM_THREADS=1)
     cores = orc.num_threads()
     wavs, secs, ntr = cpu_sample(wl, cores)
     st = msv.Settings.default(**wl["settings"])

@@ -989,6 +989,16 @@ done:
     return err ? -1 : 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm of bench.py asks for every host core explicitly. */
+ORC_API void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP

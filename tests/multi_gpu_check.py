@@ -1,0 +1,60 @@
+"""Run under torchrun on N GPUs: every rank analyses its shard of a small batch, the ranks exchange the
+dB range over NCCL in-stream, and each rank's pixels must equal what ONE process computes for the whole
+batch (bit for bit: same kernels, same global range).  Not a pytest file (needs N GPUs)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import msv_b200 as msv
+    import synth
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    srs = [48000, 44100, 22050, 48000, 16000, 8000, 48000]          # 7 tracks, mixed rates -> max_sr must be exchanged too
+    n_tracks = len(srs)
+    tracks = [synth.derive_track(synth.base_clip(4 * sr + 321, sr, seed=100 + sr), t) for t, sr in enumerate(srs)]
+    mine = msv.shard_ids(n_tracks, world, rank)
+    dev = [torch.from_numpy(tracks[t]).cuda() for t in mine]
+    sm = msv.ShardedMultiTrack(device=local)
+    sm.add_tracks_device(mine, [d.data_ptr() for d in dev], [d.numel() for d in dev], [srs[t] for t in mine], keepalive=dev)
+    outs = []
+    for t in mine:
+        w = sm.mt.image_width(t, 100.0)
+        outs.append(torch.empty(w * 300 * 4, dtype=torch.uint8, device="cuda"))
+    sm.render_device(mine, 100.0, 300, 4, [o.data_ptr() for o in outs], [o.numel() for o in outs])
+    sm.synchronize()
+    got_range = (sm.get_max_db(), sm.get_min_db())
+    # single-process answer for the whole batch on this rank's GPU
+    ref = msv.MultiTrack(device=local)
+    ref.add_tracks_pcm(list(range(n_tracks)), tracks, srs)
+    want_range = (ref.get_max_db(), ref.get_min_db())
+    ok = got_range == want_range
+    for t, o in zip(mine, outs):
+        want = ref.get_spec_image_rgba(t, 100.0, 300)
+        same = np.array_equal(o.cpu().numpy(), want)
+        ok = ok and same
+        print(f"rank {rank}: track {t} sr={srs[t]} pixels identical to single-process: {same}", flush=True)
+    print(f"rank {rank}: range sharded {got_range} single {want_range}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    sm.close(); ref.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI-GPU CHECK", "PASSED" if int(flag.item()) == 1 else "FAILED", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -253,6 +253,9 @@ class Oracle:
     def num_threads(self):
         return self.lib.orc_num_threads()
 
+    def set_num_threads(self, n):
+        self.lib.orc_set_num_threads(int(n))
+
     # ---- whole pipeline (MultiTrack::add_tracks + get_spec_image for all tracks) ---------------
     def pipeline(self, wavs, srs, params, windows, mel_fbs, mel_scale=True, db_range=120.0, px_per_sec=100.0, nheight=500,
                  channels=3, dense_mel=False, parallel_render=True, render=True):
