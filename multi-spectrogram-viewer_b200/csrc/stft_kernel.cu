@@ -454,9 +454,8 @@ stft_db_kernel(const StftLaunch L)
         };
 
         // one conjugate-symmetric pair: a = Z[k], b = Z[h-k], k <= h/2 -> X[k] and (optionally) X[h-k]
-        auto split_pair = [&](int k, const float (&ar)[V], const float (&ai)[V], const float (&br)[V],
+        auto split_pair = [&](int k, float2 cs, const float (&ar)[V], const float (&ai)[V], const float (&br)[V],
                               const float (&bi)[V], bool emit_partner) {
-            const float2 cs = __ldg(L.split + k); // (cos, sin)(k pi / h)
             float xr[V], xi[V], yr[V], yi[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -489,6 +488,15 @@ stft_db_kernel(const StftLaunch L)
                 bB[p] = (p == 0 && gt == 0) ? NSL / 2 : NSL - bA[p];          // thread 0 also owns NSL/2
                 wA[p] = __ldg(L.tw + bA[p]); wB[p] = __ldg(L.tw + bB[p]);     // exp(-2 pi i j / H)
             }
+            // split twiddles (cos, sin)(k pi / h) of the bins this thread will finish, fetched up front
+            float2 csA[NPR][RL / 2], csB[NPR][RL / 2];
+#pragma unroll
+            for (int p = 0; p < NPR; ++p)
+#pragma unroll
+                for (int r = 0; r < RL / 2; ++r) {
+                    csA[p][r] = __ldg(L.split + bA[p] + r * NSL);
+                    csB[p][r] = __ldg(L.split + bB[p] + r * NSL);
+                }
 #pragma unroll
             for (int p = 0; p < NPR; ++p) {
                 const int sa = padi(bA[p]) * V, sb = padi(bB[p]) * V;
@@ -529,20 +537,20 @@ stft_db_kernel(const StftLaunch L)
                 const int ba = (2 * p) * RL, bb = (2 * p + 1) * RL; // register blocks of butterflies bA, bB
                 if (p == 0 && gt == 0) {
                     // butterfly 0 pairs with itself: Z[r NSL] <-> Z[(RL - r) NSL]; r = 0 and r = RL/2 are self-conjugate
-                    split_pair(0, re[ba], im[ba], re[ba], im[ba], true);
+                    split_pair(0, csA[p][0], re[ba], im[ba], re[ba], im[ba], true);
 #pragma unroll
                     for (int r = 1; r < RL / 2; ++r)
-                        split_pair(r * NSL, re[ba + r], im[ba + r], re[ba + RL - r], im[ba + RL - r], true);
-                    split_pair(H / 2, re[ba + RL / 2], im[ba + RL / 2], re[ba + RL / 2], im[ba + RL / 2], false);
+                        split_pair(r * NSL, csA[p][r], re[ba + r], im[ba + r], re[ba + RL - r], im[ba + RL - r], true);
+                    split_pair(H / 2, make_float2(0.0f, 1.0f), re[ba + RL / 2], im[ba + RL / 2], re[ba + RL / 2], im[ba + RL / 2], false);
                     // butterfly NSL/2 pairs with itself: Z[NSL/2 + r NSL] <-> Z[NSL/2 + (RL-1-r) NSL]
 #pragma unroll
                     for (int r = 0; r < RL / 2; ++r)
-                        split_pair(NSL / 2 + r * NSL, re[bb + r], im[bb + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
+                        split_pair(NSL / 2 + r * NSL, csB[p][r], re[bb + r], im[bb + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
                 } else {
 #pragma unroll
                     for (int r = 0; r < RL / 2; ++r) {
-                        split_pair(bA[p] + r * NSL, re[ba + r], im[ba + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
-                        split_pair(bB[p] + r * NSL, re[bb + r], im[bb + r], re[ba + RL - 1 - r], im[ba + RL - 1 - r], true);
+                        split_pair(bA[p] + r * NSL, csA[p][r], re[ba + r], im[ba + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
+                        split_pair(bB[p] + r * NSL, csB[p][r], re[bb + r], im[bb + r], re[ba + RL - 1 - r], im[ba + RL - 1 - r], true);
                     }
                 }
             }
@@ -584,46 +592,65 @@ stft_db_kernel(const StftLaunch L)
         } // !FUSED
 
         // ---- banded mel projection + dB -----------------------------------------------------------
-        // Work item = (filter m, lane pl of the 2^lg lanes sharing it); the tap loop runs to the warp's
-        // longest band with predicated loads so that it can be unrolled and the loads overlap.
+        // Work item = (filter m, lane pl of the 2^lg lanes sharing it).  Up to kMelRounds rounds of items
+        // are processed TOGETHER: their descriptors are fetched before the barrier, the tap loop runs to
+        // the warp's longest band with predicated loads and carries one independent accumulator set
+        // per round, so several table loads are always in flight.
         if (mode == MODE_MEL_DB) {
-            group_sync<G, NT>(grp);
+            constexpr int kMelRounds = 3;
             const int lg = td->mel_log2p, P = 1 << lg;
             const int items = n_out << lg;
             const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo); // {lo, cnt, off, 0}
             const float *__restrict__ mw = td->mel_w;
-            for (int w0 = 0; w0 < items; w0 += NT) {
-                const int wi = w0 + gt;
-                const int m = wi >> lg, pl = wi & (P - 1);
-                const bool valid = m < n_out;
-                const int4 mt = valid ? __ldg(meta + m) : make_int4(0, 0, 0, 0);
-                const int nj = mt.y > pl ? (mt.y - pl + P - 1) >> lg : 0; // taps of this lane: pl, pl+P, ...
-                const int njmax = __reduce_max_sync(0xffffffffu, nj);
-                const float *__restrict__ wp = mw + mt.z + pl;
-                const int bin0 = mt.x + pl;
-                float acc[V];
+            for (int w0 = 0; w0 < items; w0 += kMelRounds * NT) {
+                int mm[kMelRounds], nj[kMelRounds], bin0[kMelRounds];
+                const float *wp[kMelRounds];
+                int njall = 0;
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc[v] = 0.0f;
-#pragma unroll 4
-                for (int j = 0; j < njmax; ++j) {
-                    const bool on = j < nj;
-                    const float wgt = on ? __ldg(wp + (j << lg)) : 0.0f;
-                    float mg[V];
-                    ld_vec<V>(sre + padi(on ? bin0 + (j << lg) : 0) * V, mg);
-#pragma unroll
-                    for (int v = 0; v < V; ++v) acc[v] = fmaf(mg[v], wgt, acc[v]);
+                for (int r = 0; r < kMelRounds; ++r) {
+                    const int wi = w0 + r * NT + gt;
+                    const int m = wi >> lg, pl = wi & (P - 1);
+                    const bool valid = wi < items;
+                    const int4 mt = valid ? __ldg(meta + m) : make_int4(0, 0, 0, 0);
+                    mm[r] = valid ? m : -1;
+                    nj[r] = mt.y > pl ? (mt.y - pl + P - 1) >> lg : 0; // taps of this lane: pl, pl+P, ...
+                    wp[r] = mw + mt.z + pl;
+                    bin0[r] = mt.x + pl;
+                    njall = max(njall, nj[r]);
                 }
-                for (int s = P >> 1; s > 0; s >>= 1)
+                if (w0 == 0) group_sync<G, NT>(grp); // magnitudes of all bins are in the buffer
+                const int njmax = __reduce_max_sync(0xffffffffu, njall);
+                float acc[kMelRounds][V];
 #pragma unroll
-                    for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], s);
-                if (valid && pl == 0) {
+                for (int r = 0; r < kMelRounds; ++r)
 #pragma unroll
-                    for (int v = 0; v < V; ++v)
-                        if (fl0 + v < nfr) {
-                            const float y = amp_to_db_dev(acc[v]);
-                            vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
-                            out[(size_t)(t0 + fl0 + v) * n_out + m] = y;
-                        }
+                    for (int v = 0; v < V; ++v) acc[r][v] = 0.0f;
+#pragma unroll 2
+                for (int j = 0; j < njmax; ++j) {
+#pragma unroll
+                    for (int r = 0; r < kMelRounds; ++r) {
+                        const bool on = j < nj[r];
+                        const float wgt = on ? __ldg(wp[r] + (j << lg)) : 0.0f;
+                        float mg[V];
+                        ld_vec<V>(sre + padi(on ? bin0[r] + (j << lg) : 0) * V, mg);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[r][v] = fmaf(mg[v], wgt, acc[r][v]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kMelRounds; ++r) {
+                    for (int s = P >> 1; s > 0; s >>= 1)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[r][v] += __shfl_xor_sync(0xffffffffu, acc[r][v], s);
+                    if (mm[r] >= 0 && ((w0 + r * NT + gt) & (P - 1)) == 0) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            if (fl0 + v < nfr) {
+                                const float y = amp_to_db_dev(acc[r][v]);
+                                vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+                                out[(size_t)(t0 + fl0 + v) * n_out + mm[r]] = y;
+                            }
+                    }
                 }
             }
         }
