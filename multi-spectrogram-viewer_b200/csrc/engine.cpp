@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -402,7 +403,8 @@ AxisTableDev *MultiTrack::axis_table(int n_in, int n_out, bool tap_major)
         axis_.clear();
     }
     std::unique_ptr<AxisTableDev> t(new AxisTableDev());
-    t->taps = (int)lanczos3_max_taps((uint32_t)n_in, (uint32_t)n_out);
+    // the fast render kernels read 8 or 16 taps per output index unconditionally: rows are at least 16 wide, zero-filled
+    t->taps = (std::max(16, (int)lanczos3_max_taps((uint32_t)n_in, (uint32_t)n_out)) + 3) & ~3;
     t->left.alloc(n_out); t->cnt.alloc(n_out); t->sum.alloc(n_out);
     t->w.alloc((size_t)n_out * t->taps);
     SGX_CUDA(launch_build_axis_table(n_in, n_out, t->taps, tap_major, t->left.p, t->cnt.p, t->sum.p, t->w.p, stream_));
@@ -466,7 +468,7 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
                 L.tracks = d_render_.p + c; L.n_tracks = (int)std::min<size_t>(65535, b - c);
                 L.from_db = 1; L.range = d_state_.p; L.channels = channels;
                 L.px = tl.px; L.py = tl.py; L.fc = tl.fc; L.rv_max = tl.rv_max;
-                SGX_CUDA(launch_render(L, items[a].nwidth, (int)nheight, tl.smem_bytes, tl.fast != 0, stream_));
+                SGX_CUDA(launch_render(L, items[a].nwidth, (int)nheight, tl.smem_bytes, tl.fast, stream_));
             }
             a = b;
         }
@@ -614,7 +616,8 @@ void stage_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint3
     DevBuf<uint8_t> dout; dout.alloc(need);
     SGX_CUDA(cudaMemcpyAsync(dg.p, grey, (size_t)width * height * sizeof(float), cudaMemcpyHostToDevice, s));
     AxisTableDev v, h;
-    v.taps = (int)lanczos3_max_taps(height, nheight); h.taps = (int)lanczos3_max_taps(width, nwidth);
+    v.taps = (std::max(16, (int)lanczos3_max_taps(height, nheight)) + 3) & ~3;
+    h.taps = (std::max(16, (int)lanczos3_max_taps(width, nwidth)) + 3) & ~3;
     v.left.alloc(nheight); v.cnt.alloc(nheight); v.sum.alloc(nheight); v.w.alloc((size_t)nheight * v.taps);
     h.left.alloc(nwidth); h.cnt.alloc(nwidth); h.sum.alloc(nwidth); h.w.alloc((size_t)nwidth * h.taps);
     SGX_CUDA(launch_build_axis_table((int)height, (int)nheight, v.taps, false, v.left.p, v.cnt.p, v.sum.p, v.w.p, s));
@@ -629,7 +632,7 @@ void stage_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint3
     RenderLaunch L{};
     L.tracks = dr.p; L.n_tracks = 1; L.from_db = 0; L.range = nullptr; L.channels = channels;
     L.px = tl.px; L.py = tl.py; L.fc = tl.fc; L.rv_max = tl.rv_max;
-    SGX_CUDA(launch_render(L, (int)nwidth, (int)nheight, tl.smem_bytes, tl.fast != 0, s));
+    SGX_CUDA(launch_render(L, (int)nwidth, (int)nheight, tl.smem_bytes, tl.fast, s));
     SGX_CUDA(cudaMemcpyAsync(out, dout.p, need, cudaMemcpyDeviceToHost, s));
     SGX_CUDA(cudaStreamSynchronize(s));
 }

@@ -53,7 +53,7 @@ cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_majo
 struct RenderTiling { int px, py, fc, rv_max; size_t smem_bytes; int fast; };
 RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight);
 cudaError_t launch_render(const RenderLaunch &launch, int max_nwidth, int max_nheight,
-                          size_t smem_bytes, bool fast, cudaStream_t s);
+                          size_t smem_bytes, int fast, cudaStream_t s);
 
 // small elementwise kernels of the stage API
 cudaError_t launch_spec_to_grey(const float *spec, int n_frames, int n_out, int height, float max_db,

@@ -271,11 +271,15 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaun
 // distinct 16-byte bank groups while neighbouring lanes address neighbouring (or equal) rows.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kFpTile = 64;     // output pixels per tile edge
-constexpr int kFpTaps = 8;
-constexpr int kFpCap = 84;      // source frames / rows a tile can need: 63 * 1.16 + 8 = 81.1, rounded to 4
-constexpr int kFpGP = 84;       // pitch of G  [row][frame]
-constexpr int kFpTP = 68;       // pitch of Tm [frame][out row]
-constexpr size_t kFpSmem = (size_t)(kFpCap * kFpGP + kFpCap * kFpTP) * sizeof(float);
+constexpr int kFpTP = 68;       // pitch of Tm [frame][out row]  (odd multiple of 4)
+// source frames / rows a tile can need with T taps per output index (n_in/n_out < (T-1)/6):
+// 63 * ratio + T, rounded up to a multiple of 4 whose quarter is odd (conflict-free 128-bit phases)
+__host__ __device__ constexpr int fp_cap(int taps) { return taps <= 8 ? 84 : 164; }
+__host__ __device__ constexpr float fp_max_ratio(int taps) { return taps <= 8 ? 1.16f : 2.33f; }
+__host__ __device__ constexpr size_t fp_smem(int tv, int th)
+{
+    return (size_t)(fp_cap(tv) * fp_cap(th) + fp_cap(th) * kFpTP) * sizeof(float);
+}
 
 // display.rs:24-42 with the colour map stored as (a, b) = (stop i, stop i+1) pairs per channel.
 // round() is floor(v + 0.5): identical to f32::round for v >= 0 except within 2^-25 below 0.5.
@@ -294,12 +298,14 @@ __device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const float2 *cma
     return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
 }
 
-__global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const RenderLaunch L)
+template <int TV, int TH, bool FROM_DB, int CH>
+__global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? 4 : 1) render_fast_kernel(const RenderLaunch L)
 {
+    constexpr int RCAP = fp_cap(TV), FCAP = fp_cap(TH), GP = FCAP; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
     __shared__ float2 cmab[27];
-    float *G = rsm;                      // [row][frame]
-    float *Tm = rsm + kFpCap * kFpGP;    // [frame][out row]
+    float *G = rsm;
+    float *Tm = rsm + RCAP * GP;         // [frame][out row]
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
     const int nwidth = tr->nwidth, nheight = tr->nheight;
     const int ox0 = blockIdx.x * kFpTile, oy0 = blockIdx.y * kFpTile;
@@ -314,52 +320,63 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
     const int width = tr->width, height = tr->height, n_out = tr->n_out;
 
     const int fl = __ldg(h_left + ox0);
-    const int nfr = min(__ldg(h_left + ox0 + pxc - 1) + kFpTaps - fl, kFpCap);
+    const int nfr = min(__ldg(h_left + ox0 + pxc - 1) + TH - fl, FCAP);
     const int nfq = (nfr + 3) >> 2;                 // frame quads
     const int yl = __ldg(v_left + oy0);
-    const int nrow = min(__ldg(v_left + oy0 + pyc - 1) + kFpTaps - yl, kFpCap);
+    const int nrow = min(__ldg(v_left + oy0 + pyc - 1) + TV - yl, RCAP);
 
     // weights of phases B and C first: their global loads complete while phase A runs
     const int oyl_b = (warp & 1) * 32 + lane;
     const int oy_b = oy0 + min(oyl_b, pyc - 1);
     const int oxl_c = (warp & 1) * 32 + lane;
     const int ox_c = ox0 + min(oxl_c, pxc - 1);
-    float wv[kFpTaps], wh[kFpTaps];
+    float wv[TV], wh[TH];
     {
-        const float *__restrict__ wrow = tr->v_w + (size_t)oy_b * tr->v_taps;
+        // v_w rows are 16-byte aligned (row width is a multiple of 4 floats, >= 16)
+        const float4 *__restrict__ wrow = reinterpret_cast<const float4 *>(tr->v_w + (size_t)oy_b * tr->v_taps);
 #pragma unroll
-        for (int i = 0; i < kFpTaps; ++i) { wv[i] = __ldg(wrow + i); wh[i] = __ldg(tr->h_w + (size_t)i * nwidth + ox_c); }
+        for (int i = 0; i < TV / 4; ++i) {
+            const float4 q = __ldg(wrow + i);
+            wv[4 * i] = q.x; wv[4 * i + 1] = q.y; wv[4 * i + 2] = q.z; wv[4 * i + 3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TH; ++i) wh[i] = __ldg(tr->h_w + (size_t)i * nwidth + ox_c);
     }
     const float vsum = __ldg(tr->v_sum + oy_b), hsum = __ldg(tr->h_sum + ox_c);
     const int voff = __ldg(v_left + oy_b) - yl, hoff = __ldg(h_left + ox_c) - fl;
 
     // ---- A: grey tile ------------------------------------------------------------------------------
     float min_db = 0.0f, inv_span = 0.0f;
-    if (L.from_db) { min_db = L.range[1]; inv_span = __frcp_rn(L.range[0] - L.range[1]); }
-    const int pad_rows = height - n_out; // rows above the spectrogram are 0 (display.rs:47-52)
+    if (FROM_DB) { min_db = L.range[1]; inv_span = __frcp_rn(L.range[0] - L.range[1]); }
     {
+        // rows of the tile that hold data: grey rows [pad_rows, height) (display.rs:47-52), in tile coordinates
+        const int pad_rows = FROM_DB ? height - n_out : 0;
+        const int yy_lo = max(pad_rows - yl, 0), yy_hi = min(height - yl, nrow);
         const int fsub = lane & 3, rsub = lane >> 2;
-        constexpr int kRowBatches = (kFpCap + 7) / 8;
         for (int fq = warp; fq < nfq; fq += kRenderThreads / 32) {
             const int fx = fq * 4 + fsub;
             const int f = fl + fx;
             const bool fok = f < width;
-            const float *__restrict__ col = src + (size_t)(fok ? f : 0) * n_out + (height - 1);
-            // all loads of this frame quad are issued before the first use (memory-level parallelism)
-            float v[kRowBatches];
+            // FROM_DB: element (frame f, grey row y) is dB[f][height-1-y]; else grey[y][f]
+            const float *__restrict__ p0 = FROM_DB ? src + (size_t)(fok ? f : 0) * n_out + (height - 1 - yl - rsub)
+                                                   : src + (size_t)(yl + rsub) * width + (fok ? f : 0);
+            float *g0 = G + rsub * GP + fx;
+            for (int j0 = 0; j0 < nrow; j0 += 32) {
+                // four 8-row batches per trip, all loads issued before the first use
+                float v[4];
 #pragma unroll
-            for (int j = 0; j < kRowBatches; ++j) {
-                const int yy = j * 8 + rsub;
-                const int y = yl + yy;
-                const bool ok = fok && yy < nrow && y < height && (!L.from_db || y >= pad_rows);
-                v[j] = L.from_db ? -INFINITY : 0.0f; // -inf -> grey 0 after the saturate
-                if (ok) v[j] = L.from_db ? __ldg(col - y) : __ldg(src + (size_t)y * width + f);
-            }
+                for (int j = 0; j < 4; ++j) {
+                    const int yy = j0 + j * 8 + rsub;
+                    const bool ok = fok && yy >= yy_lo && yy < yy_hi;
+                    v[j] = FROM_DB ? -INFINITY : 0.0f; // -inf -> grey 0 after the saturate
+                    if (ok) v[j] = FROM_DB ? __ldg(p0 - (j0 + j * 8)) : __ldg(p0 + (size_t)(j0 + j * 8) * width);
+                }
 #pragma unroll
-            for (int j = 0; j < kRowBatches; ++j) {
-                const int yy = j * 8 + rsub;
-                const float g = L.from_db ? __saturatef((v[j] - min_db) * inv_span) : v[j];
-                if (yy < kFpCap && j * 8 < nrow) G[yy * kFpGP + fx] = g;
+                for (int j = 0; j < 4; ++j) {
+                    const int yy = j0 + j * 8 + rsub;
+                    const float g = FROM_DB ? __saturatef((v[j] - min_db) * inv_span) : v[j];
+                    if (yy < RCAP) g0[(j0 + j * 8) * GP] = g;
+                }
             }
         }
     }
@@ -369,18 +386,17 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
     {
         const int oyl = oyl_b;
         const float rs = __frcp_rn(vsum);
-        float w[kFpTaps];
 #pragma unroll
-        for (int i = 0; i < kFpTaps; ++i) w[i] = wv[i] * rs;
-        const float *g = G + voff * kFpGP;
+        for (int i = 0; i < TV; ++i) wv[i] *= rs;
+        const float *g = G + voff * GP;
         if (oyl < pyc) {
             for (int fq = warp >> 1; fq < nfq; fq += kRenderThreads / 64) {
                 float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
 #pragma unroll
-                for (int i = 0; i < kFpTaps; ++i) {
-                    const float4 v = *reinterpret_cast<const float4 *>(g + i * kFpGP + fq * 4);
-                    t0 = fmaf(v.x, w[i], t0); t1 = fmaf(v.y, w[i], t1);
-                    t2 = fmaf(v.z, w[i], t2); t3 = fmaf(v.w, w[i], t3);
+                for (int i = 0; i < TV; ++i) {
+                    const float4 v = *reinterpret_cast<const float4 *>(g + i * GP + fq * 4);
+                    t0 = fmaf(v.x, wv[i], t0); t1 = fmaf(v.y, wv[i], t1);
+                    t2 = fmaf(v.z, wv[i], t2); t3 = fmaf(v.w, wv[i], t3);
                 }
                 float *t_out = Tm + (fq * 4) * kFpTP + oyl;
                 t_out[0] = clamp_pos(t0); t_out[kFpTP] = clamp_pos(t1);
@@ -394,9 +410,8 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
     {
         const int oxl = oxl_c, ox = ox_c;
         const float rs = __frcp_rn(hsum);
-        float w[kFpTaps];
 #pragma unroll
-        for (int i = 0; i < kFpTaps; ++i) w[i] = wh[i] * rs;
+        for (int i = 0; i < TH; ++i) wh[i] *= rs;
         const float *t_in = Tm + hoff * kFpTP;
         unsigned char *__restrict__ outp = tr->out;
         if (oxl < pxc) {
@@ -404,18 +419,17 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_fast_kernel(const Re
             for (int rq = warp >> 1; rq < nrq; rq += kRenderThreads / 64) {
                 float t[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int i = 0; i < kFpTaps; ++i) {
+                for (int i = 0; i < TH; ++i) {
                     const float4 v = *reinterpret_cast<const float4 *>(t_in + i * kFpTP + rq * 4);
-                    t[0] = fmaf(v.x, w[i], t[0]); t[1] = fmaf(v.y, w[i], t[1]);
-                    t[2] = fmaf(v.z, w[i], t[2]); t[3] = fmaf(v.w, w[i], t[3]);
+                    t[0] = fmaf(v.x, wh[i], t[0]); t[1] = fmaf(v.y, wh[i], t[1]);
+                    t[2] = fmaf(v.z, wh[i], t[2]); t[3] = fmaf(v.w, wh[i], t[3]);
                 }
+                size_t pix = (size_t)(oy0 + rq * 4) * nwidth + ox;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int oyl = rq * 4 + j;
-                    if (oyl < pyc) {
+                for (int j = 0; j < 4; ++j, pix += nwidth) {
+                    if (rq * 4 + j < pyc) {
                         const unsigned c = grey_to_rgba_fast(clamp_pos(t[j]), cmab);
-                        const size_t pix = (size_t)(oy0 + oyl) * nwidth + ox;
-                        if (L.channels == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
+                        if (CH == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
                         else { outp[pix * 3] = (unsigned char)c; outp[pix * 3 + 1] = (unsigned char)(c >> 8); outp[pix * 3 + 2] = (unsigned char)(c >> 16); }
                     }
                 }
@@ -550,11 +564,13 @@ cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_majo
 
 RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
 {
-    // fast path: at most 8 taps per output index on both axes (same f32 ratio the tap tables use)
+    // fast path: at most 8 / 16 taps per output index on each axis (same f32 ratio the tap tables use)
     const float rhf = (float)width / (float)nwidth, rvf = (float)height / (float)nheight;
-    if (rhf < 1.16f && rvf < 1.16f) {
+    if (rhf < fp_max_ratio(16) && rvf < fp_max_ratio(16)) {
+        const int th = rhf < fp_max_ratio(8) ? 8 : 16, tv = rvf < fp_max_ratio(8) ? 8 : 16;
         RenderTiling t{};
-        t.px = kFpTile; t.py = kFpTile; t.fc = kFpCap; t.rv_max = kFpCap; t.smem_bytes = kFpSmem; t.fast = 1;
+        t.px = kFpTile; t.py = kFpTile; t.fc = fp_cap(th); t.rv_max = fp_cap(tv); t.smem_bytes = fp_smem(tv, th);
+        t.fast = tv * 100 + th;
         return t;
     }
     // frames a tile of px output columns needs, rows a tile of py output rows needs
@@ -593,19 +609,30 @@ RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
 }
 
 cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight, size_t smem_bytes,
-                          bool fast, cudaStream_t s)
+                          int fast, cudaStream_t s)
 {
     if (L.n_tracks <= 0 || max_nwidth <= 0 || max_nheight <= 0) return cudaSuccess;
     if (fast) {
-        static bool fast_configured = false;
-        if (!fast_configured) {
-            cudaError_t e = cudaFuncSetAttribute(render_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)kFpSmem);
-            if (e != cudaSuccess) return e;
-            fast_configured = true;
-        }
         dim3 grid((max_nwidth + kFpTile - 1) / kFpTile, (max_nheight + kFpTile - 1) / kFpTile, L.n_tracks);
-        render_fast_kernel<<<grid, kRenderThreads, kFpSmem, s>>>(L);
+        const int tv = fast / 100, th = fast % 100;
+        cudaError_t err = cudaErrorInvalidValue;
+#define SGX_FAST(TV, TH, DB, CHN)                                                                             \
+        if (tv == TV && th == TH && (L.from_db != 0) == DB && L.channels == CHN) {                           \
+            auto kern = render_fast_kernel<TV, TH, DB, CHN>;                                                  \
+            static bool configured = false;                                                                   \
+            if (!configured) {                                                                                \
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem(TV, TH)); \
+                if (e != cudaSuccess) return e;                                                               \
+                configured = true;                                                                            \
+            }                                                                                                 \
+            kern<<<grid, kRenderThreads, fp_smem(TV, TH), s>>>(L);                                            \
+            err = cudaSuccess;                                                                                \
+        }
+#define SGX_FAST4(TV, TH) SGX_FAST(TV, TH, true, 4) SGX_FAST(TV, TH, true, 3) SGX_FAST(TV, TH, false, 4) SGX_FAST(TV, TH, false, 3)
+        SGX_FAST4(8, 8) SGX_FAST4(8, 16) SGX_FAST4(16, 8) SGX_FAST4(16, 16)
+#undef SGX_FAST4
+#undef SGX_FAST
+        if (err != cudaSuccess) return err;
         count_launch();
         return cudaGetLastError();
     }
