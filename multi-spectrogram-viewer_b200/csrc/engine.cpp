@@ -87,11 +87,14 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
     tt.win_f.upload(wf.data(), n_fft, s);
     if (mel_fb) {
         const int tpg = cfg.generic ? 1 : cfg.h / cfg.pts;
-        MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg);
+        // capacity of the imaginary plane of one group's exchange buffer (floats), where K1 stages the bank
+        const size_t plane = cfg.generic ? 0 : cfg.fft_smem / sizeof(float) / (2 * (size_t)cfg.groups);
+        MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg, plane);
         if (cfg.generic) mb.log2_split = 0;
         std::vector<int> meta(4 * n_mel, 0); // {lo, cnt, off, 0} per filter: one 16-byte load on the device
         for (size_t m = 0; m < n_mel; ++m) { meta[4 * m] = mb.lo[m]; meta[4 * m + 1] = mb.cnt[m]; meta[4 * m + 2] = mb.off[m]; }
         tt.mel_lo.upload(meta.data(), meta.size(), s);
+        tt.mel_cnt.upload(mb.sched.data(), mb.sched.size(), s);
         tt.mel_w.upload(mb.w.data(), mb.w.size(), s);
         tt.mel_log2p = mb.log2_split;
     }

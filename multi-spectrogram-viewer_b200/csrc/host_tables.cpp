@@ -167,7 +167,8 @@ uint32_t grey_height(size_t n_out, float up_ratio)
     return (uint32_t)std::round((float)n_out * up_ratio);
 }
 
-MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group)
+MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group,
+                        size_t stage_capacity_floats)
 {
     MelBands mb;
     mb.lo.resize(n_mel); mb.cnt.resize(n_mel); mb.off.resize(n_mel);
@@ -198,6 +199,32 @@ MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int thread
         if (cost < best_cost) { best_cost = cost; best = lg; }
     }
     mb.log2_split = best;
+    // block schedule: 32 consecutive work items (filter, lane-of-filter) per block, blocks packed
+    // longest-first onto the warps of a thread group
+    const int P = 1 << best, warps = std::max(1, threads_per_group / 32);
+    const size_t n_items = n_mel * (size_t)P, n_blocks = (n_items + 31) / 32;
+    std::vector<std::pair<int, int>> cost(n_blocks); // (cost, block)
+    for (size_t b = 0; b < n_blocks; ++b) {
+        int longest = 0;
+        for (size_t it = b * 32; it < std::min(n_items, (b + 1) * 32); ++it)
+            longest = std::max(longest, (mb.cnt[it / P] + P - 1) / P);
+        cost[b] = {longest + 4, (int)b};
+    }
+    std::sort(cost.begin(), cost.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+    std::vector<std::vector<int>> lists(warps);
+    std::vector<long> load(warps, 0);
+    for (auto &c : cost) {
+        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        lists[w].push_back(c.second); load[w] += c.first;
+    }
+    size_t slots = 0;
+    for (auto &l : lists) slots = std::max(slots, l.size());
+    const size_t nnz = mb.w.size();
+    const bool staged = ((nnz + 3) & ~(size_t)3) + 4 * n_mel <= stage_capacity_floats;
+    mb.sched.assign(4 + slots * warps, -1);
+    mb.sched[0] = (int)slots; mb.sched[1] = (int)nnz; mb.sched[2] = staged ? 1 : 0; mb.sched[3] = 0;
+    for (int w = 0; w < warps; ++w)
+        for (size_t i = 0; i < lists[w].size(); ++i) mb.sched[4 + i * warps + w] = lists[w][i];
     return mb;
 }
 

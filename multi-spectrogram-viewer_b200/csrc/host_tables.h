@@ -37,7 +37,9 @@ struct MelBands {
     std::vector<float> w;          // taps, filter-major
     int max_cnt = 0;
     int log2_split = 0;            // lanes cooperating on one filter (power of two <= 32)
+    std::vector<int> sched;        // {slots, taps, staged, 0, block ids [slots][warps]}: balanced block lists per warp
 };
-MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group);
+MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group,
+                        size_t stage_capacity_floats);
 
 } // namespace sgx

@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -592,66 +593,68 @@ stft_db_kernel(const StftLaunch L)
         } // !FUSED
 
         // ---- banded mel projection + dB -----------------------------------------------------------
-        // Work item = (filter m, lane pl of the 2^lg lanes sharing it).  Up to kMelRounds rounds of items
-        // are processed TOGETHER: their descriptors are fetched before the barrier, the tap loop runs to
-        // the warp's longest band with predicated loads and carries one independent accumulator set
-        // per round, so several table loads are always in flight.
+        // Work item = (filter m, lane pl of the 2^lg lanes sharing it); 32 consecutive items form a block
+        // and the host hands every warp of the group a balanced list of blocks (longest-first packing).
+        // The filterbank taps and descriptors are first staged in the imaginary plane of the exchange
+        // buffer -- it is dead once the spectrum has been read -- so the tap loop only touches shared memory.
         if (mode == MODE_MEL_DB) {
-            constexpr int kMelRounds = 3;
+            constexpr int NWARPS = NT / 32;
+            const int *__restrict__ sched = td->mel_cnt; // {slots, taps, staged, 0, block ids [slots][NWARPS]}
+            const int nslots = __ldg(sched), nnz = __ldg(sched + 1);
+            const bool staged = __ldg(sched + 2) != 0;
             const int lg = td->mel_log2p, P = 1 << lg;
-            const int items = n_out << lg;
             const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo); // {lo, cnt, off, 0}
             const float *__restrict__ mw = td->mel_w;
-            for (int w0 = 0; w0 < items; w0 += kMelRounds * NT) {
-                int mm[kMelRounds], nj[kMelRounds], bin0[kMelRounds];
-                const float *wp[kMelRounds];
-                int njall = 0;
+            float *wsm = sim;
+            int4 *msm = reinterpret_cast<int4 *>(sim + ((nnz + 3) & ~3));
+            if (staged) {
+                if constexpr (!FUSED) group_sync<G, NT>(grp); // split pairs of other threads still read sim
+                for (int i = gt; i < nnz; i += NT) wsm[i] = __ldg(mw + i);
+                for (int i = gt; i < n_out; i += NT) msm[i] = __ldg(meta + i);
+            }
+            group_sync<G, NT>(grp); // magnitudes of all bins (and the staged tables) are in the buffer
+            const int wg = gt >> 5, lane = gt & 31;
+            auto mel_block = [&](auto staged_tag, int blk) {
+                constexpr bool ST = decltype(staged_tag)::value;
+                const int wi = blk * 32 + lane;
+                const int m = wi >> lg, pl = wi & (P - 1);
+                const bool valid = m < n_out;
+                int4 mt = make_int4(0, 0, 0, 0);
+                if (valid) mt = ST ? msm[m] : __ldg(meta + m);
+                const int nj = mt.y > pl ? (mt.y - pl + P - 1) >> lg : 0; // taps of this lane: pl, pl+P, ...
+                const int njmax = __reduce_max_sync(0xffffffffu, nj);
+                const float *wp = (ST ? wsm : mw) + mt.z + pl;
+                const int bin0 = mt.x + pl;
+                float acc[V];
 #pragma unroll
-                for (int r = 0; r < kMelRounds; ++r) {
-                    const int wi = w0 + r * NT + gt;
-                    const int m = wi >> lg, pl = wi & (P - 1);
-                    const bool valid = wi < items;
-                    const int4 mt = valid ? __ldg(meta + m) : make_int4(0, 0, 0, 0);
-                    mm[r] = valid ? m : -1;
-                    nj[r] = mt.y > pl ? (mt.y - pl + P - 1) >> lg : 0; // taps of this lane: pl, pl+P, ...
-                    wp[r] = mw + mt.z + pl;
-                    bin0[r] = mt.x + pl;
-                    njall = max(njall, nj[r]);
-                }
-                if (w0 == 0) group_sync<G, NT>(grp); // magnitudes of all bins are in the buffer
-                const int njmax = __reduce_max_sync(0xffffffffu, njall);
-                float acc[kMelRounds][V];
-#pragma unroll
-                for (int r = 0; r < kMelRounds; ++r)
-#pragma unroll
-                    for (int v = 0; v < V; ++v) acc[r][v] = 0.0f;
-#pragma unroll 2
+                for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+#pragma unroll 4
                 for (int j = 0; j < njmax; ++j) {
+                    const bool on = j < nj;
+                    float wgt = 0.0f;
+                    if (on) wgt = ST ? wp[j << lg] : __ldg(wp + (j << lg));
+                    float mg[V];
+                    ld_vec<V>(sre + padi(on ? bin0 + (j << lg) : 0) * V, mg);
 #pragma unroll
-                    for (int r = 0; r < kMelRounds; ++r) {
-                        const bool on = j < nj[r];
-                        const float wgt = on ? __ldg(wp[r] + (j << lg)) : 0.0f;
-                        float mg[V];
-                        ld_vec<V>(sre + padi(on ? bin0[r] + (j << lg) : 0) * V, mg);
-#pragma unroll
-                        for (int v = 0; v < V; ++v) acc[r][v] = fmaf(mg[v], wgt, acc[r][v]);
-                    }
+                    for (int v = 0; v < V; ++v) acc[v] = fmaf(mg[v], wgt, acc[v]);
                 }
+                for (int s = P >> 1; s > 0; s >>= 1)
 #pragma unroll
-                for (int r = 0; r < kMelRounds; ++r) {
-                    for (int s = P >> 1; s > 0; s >>= 1)
+                    for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], s);
+                if (valid && pl == 0) {
 #pragma unroll
-                        for (int v = 0; v < V; ++v) acc[r][v] += __shfl_xor_sync(0xffffffffu, acc[r][v], s);
-                    if (mm[r] >= 0 && ((w0 + r * NT + gt) & (P - 1)) == 0) {
-#pragma unroll
-                        for (int v = 0; v < V; ++v)
-                            if (fl0 + v < nfr) {
-                                const float y = amp_to_db_dev(acc[r][v]);
-                                vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
-                                out[(size_t)(t0 + fl0 + v) * n_out + mm[r]] = y;
-                            }
-                    }
+                    for (int v = 0; v < V; ++v)
+                        if (fl0 + v < nfr) {
+                            const float y = amp_to_db_dev(acc[v]);
+                            vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+                            out[(size_t)(t0 + fl0 + v) * n_out + m] = y;
+                        }
                 }
+            };
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int blk = __ldg(sched + 4 + slot * NWARPS + wg); // warp-uniform
+                if (blk < 0) continue;
+                if (staged) mel_block(std::true_type{}, blk); else mel_block(std::false_type{}, blk);
             }
         }
         group_sync<G, NT>(grp); // spectrum / magnitudes consumed before the next iteration overwrites the buffer
