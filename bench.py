@@ -272,7 +272,36 @@ def run_gpu(args, wl, rank, world, local_rank):
         e2e = {"value": e2e_tracks * n / sr * world / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host_in)),
                "d2h_bytes_per_step": int(img_bytes * e2e_tracks), "ms_per_step": float(dt.item()) * 1e3,
-               "api": "sgx_mt_add_tracks_pcm + sgx_mt_get_spec_image_rgba per track, pinned host buffers"}
+               "api": "sgx_mt_add_tracks_pcm (f32 host PCM) + sgx_mt_get_spec_image_rgba per track, pinned host buffers"}
+        # the same batch shape with 16-bit host PCM (what the WAV fixtures hold; sgx_mt_add_tracks_pcm_i16)
+        del host_in, np_in
+        base16 = torch.from_numpy(synth.base_clip_i16(n, sr, wl["seed"]))
+        host16 = []
+        for t in gids[:e2e_tracks]:
+            x = torch.roll(base16, -synth.track_gain_shift(t, n)[1])
+            if ch == 2:
+                x = torch.stack([x, torch.roll(x, 1234)], dim=1).contiguous()
+            host16.append(x.pin_memory())
+        np16 = [h.numpy() for h in host16]
+
+        def e2e16_step():
+            mt2.add_tracks_pcm(list(range(e2e_tracks)), np16, srs[:e2e_tracks])
+            for i in range(e2e_tracks):
+                need = C.c_size_t()
+                msv._check(msv._lib.sgx_mt_get_spec_image_rgba(mt2._h, i, PX_PER_SEC, NHEIGHT, host_out[i].data_ptr(), img_bytes, C.byref(need)))
+
+        e2e16_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e2e16_step()
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e["int16_pcm"] = {"value": e2e_tracks * n / sr * world / float(dt.item()), "ms_per_step": float(dt.item()) * 1e3,
+                            "h2d_bytes_per_step": int(sum(h.numel() * 2 for h in host16)),
+                            "api": "sgx_mt_add_tracks_pcm_i16 (int16 host PCM, scaled on the GPU) + sgx_mt_get_spec_image_rgba"}
         mt2.close()
 
     # parity spot check of what was timed (smoke-level; the real gate is tests/ -m gpu)

@@ -155,6 +155,8 @@ MultiTrack::~MultiTrack()
     cudaStreamSynchronize(stream_);
     tracks_.clear(); tables_.clear(); axis_.clear();
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
+    for (auto &e : copy_events_) cudaEventDestroy(e);
+    if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
     if (own_stream_) cudaStreamDestroy(stream_);
 }
 
@@ -281,6 +283,22 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         check_stft_args(s.n, pre[i].win, pre[i].hop, pre[i].n_fft, &pre[i].T);
     }
     // ---- insert tracks (lib.rs:174-187) --------------------------------------------------------------
+    // host-resident PCM is uploaded on a second stream, track by track, and every track's analysis starts as
+    // soon as its own copy has landed: H2D of track i+1 overlaps K1 of track i
+    bool pipelined = false;
+    for (const PcmSource &s : srcs) pipelined = pipelined || !s.on_device;
+    std::map<size_t, size_t> copy_event_of; // id -> index into copy_events_
+    if (pipelined) {
+        if (!copy_stream_) SGX_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        while (copy_events_.size() < ids.size() + 1) {
+            cudaEvent_t e;
+            SGX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            copy_events_.push_back(e);
+        }
+        // the upload may overwrite buffers that kernels already enqueued on stream_ still read
+        SGX_CUDA(cudaEventRecord(copy_events_[ids.size()], stream_));
+        SGX_CUDA(cudaStreamWaitEvent(copy_stream_, copy_events_[ids.size()], 0));
+    }
     for (size_t i = 0; i < ids.size(); ++i) {
         const PcmSource &s = srcs[i];
         // HashMap::insert replaces an existing id; its device buffers and range slot are re-used
@@ -296,7 +314,9 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         else {
             const size_t bytes = s.n * s.ch * esz;
             t.owned_pcm.ensure(bytes + 64);
-            SGX_CUDA(cudaMemcpyAsync(t.owned_pcm.p, s.data, bytes, cudaMemcpyHostToDevice, stream_));
+            SGX_CUDA(cudaMemcpyAsync(t.owned_pcm.p, s.data, bytes, cudaMemcpyHostToDevice, copy_stream_));
+            SGX_CUDA(cudaEventRecord(copy_events_[i], copy_stream_));
+            copy_event_of[ids[i]] = i;
             t.d_pcm = t.owned_pcm.p;
         }
         t.n_frames = (size_t)pre[i].T;
@@ -310,6 +330,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
     std::map<size_t, std::vector<size_t>> by_fft;
     for (size_t id : ids) by_fft[tracks_.at(id).n_fft].push_back(id);
     std::vector<StftTrack> descs;
+    std::vector<size_t> desc_ids;
     struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; };
     std::vector<Group> groups;
     for (auto &kv : by_fft) {
@@ -324,9 +345,10 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
             Track &t = tracks_.at(id);
             StftTrack d = make_desc(t.d_pcm, t.fmt, t.n, t.ch, t.win, t.hop, t.n_fft, t.n_frames, *t.tables,
                                     t.spec.p, t.n_out, slots_.p + 2 * t.slot);
-            d.tile_begin = g.n_tiles;
+            d.tile_begin = pipelined ? 0 : g.n_tiles; // pipelined: one launch per track
             g.n_tiles += (int)((t.n_frames + g.tiling.frames_per_tile - 1) / g.tiling.frames_per_tile);
             descs.push_back(d);
+            desc_ids.push_back(id);
             ++g.count;
         }
         groups.push_back(g);
@@ -342,7 +364,16 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
         L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
         L.tile_floats = g.tiling.tile_floats; L.tw = pl.tw.p; L.split = pl.split.p;
-        SGX_CUDA(launch_stft(pl.cfg, L, stream_));
+        if (!pipelined) { SGX_CUDA(launch_stft(pl.cfg, L, stream_)); continue; }
+        for (size_t k = 0; k < g.count; ++k) {
+            const size_t di = g.first + k;
+            const Track &t = tracks_.at(desc_ids[di]);
+            auto ce = copy_event_of.find(desc_ids[di]);
+            if (ce != copy_event_of.end()) SGX_CUDA(cudaStreamWaitEvent(stream_, copy_events_[ce->second], 0));
+            L.tracks = d_stft_.p + di; L.n_tracks = 1;
+            L.n_tiles = (int)((t.n_frames + g.tiling.frames_per_tile - 1) / g.tiling.frames_per_tile);
+            SGX_CUDA(launch_stft(pl.cfg, L, stream_));
+        }
     }
     if (profiling_) { SGX_CUDA(cudaEventRecord(ev_[1], stream_)); ev_valid_[0] = true; }
     // ---- update_spec_greys, range part (lib.rs:193-229) ------------------------------------------------

@@ -160,6 +160,8 @@ private:
     DevBuf<uint8_t> d_img_;      // staging for host-buffer image requests
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     bool profiling_ = false, ev_valid_[2] = {false, false};
+    cudaStream_t copy_stream_ = nullptr;          // H2D uploads of host-resident PCM
+    std::vector<cudaEvent_t> copy_events_;
     float max_db_, min_db_;
     float max_sec_ = 0.0f;
     size_t id_max_sec_ = 0;
