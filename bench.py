@@ -43,6 +43,11 @@ def workload(name):
         return dict(sr=48000, seconds=3600, channels=2, tracks=1, seed=3003,
                     settings=dict(win_length=4096, hop_length=256, n_fft=4096, n_mel=128),
                     desc="C3: 1 h x 48 kHz stereo, n_fft=4096 hop=256 Hann, mel-128, dB + RGBA 100 px/s x 500")
+    if name == "c2":
+        return dict(sr=48000, srs=[8000, 16000, 22050, 24000, 44100, 48000], seconds=44.032, channels=1, tracks=6, seed=2002,
+                    settings=dict(n_mel=128),
+                    desc="C2: six tracks of 44.032 s at 8/16/22.05/24/44.1/48 kHz (the reference's fixture rates, synthetic PCM), "
+                         "per-rate W/hop/n_fft of lib.rs:43-46, 128-band mel, dB + RGBA 100 px/s x 500")
     if name == "c1":
         return dict(sr=48000, seconds=44.031854, channels=1, tracks=1, seed=1001,
                     settings=dict(win_length=2048, hop_length=512, n_fft=2048, freq_scale=0),
@@ -176,29 +181,35 @@ def run_gpu(args, wl, rank, world, local_rank):
     st = msv.Settings.default(**wl["settings"])
 
     # ---- synthetic batch, derived on the device from one uploaded base clip ----
-    base_h = synth.base_clip(n, sr, wl["seed"])
-    base = torch.from_numpy(base_h).to(dev)
     gids = [rank + i * world for i in range(ntr)]  # track t -> GPU t mod G
     tracks = []
-    for t in gids:
-        gain, shift = synth.track_gain_shift(t, n)
-        x = torch.roll(base, -shift) * float(gain)
-        if ch == 2:
-            x = torch.stack([x, torch.roll(x, 1234) * 0.75], dim=1).contiguous()
-        tracks.append(x)
-    del base
+    if "srs" in wl:  # mixed sample rates: one clip per rate (every GPU holds the same six tracks)
+        srs = list(wl["srs"])
+        ns = [int(round(wl["seconds"] * r)) for r in srs]
+        for i, (r, m) in enumerate(zip(srs, ns)):
+            tracks.append(torch.from_numpy(synth.derive_track(synth.base_clip(m, r, wl["seed"] + r), i)).to(dev))
+    else:
+        base_h = synth.base_clip(n, sr, wl["seed"])
+        base = torch.from_numpy(base_h).to(dev)
+        for t in gids:
+            gain, shift = synth.track_gain_shift(t, n)
+            x = torch.roll(base, -shift) * float(gain)
+            if ch == 2:
+                x = torch.stack([x, torch.roll(x, 1234) * 0.75], dim=1).contiguous()
+            tracks.append(x)
+        del base
+        ns = [n] * ntr
+        srs = [sr] * ntr
     sm = msv.ShardedMultiTrack(st, device=local_rank)
     sm.mt.set_profiling(True)
     ids = list(range(ntr))
     ptrs = [x.data_ptr() for x in tracks]
-    ns = [n] * ntr
-    srs = [sr] * ntr
     chs = [ch] * ntr
-    nwidth = int(np.float32(PX_PER_SEC) * np.float32(n) / np.float32(sr))
-    img_bytes = nwidth * NHEIGHT * 4
-    outs = [torch.empty(img_bytes, dtype=torch.uint8, device=dev) for _ in range(ntr)]
+    nwidths = [int(np.float32(PX_PER_SEC) * np.float32(m) / np.float32(r)) for m, r in zip(ns, srs)]
+    caps = [w * NHEIGHT * 4 for w in nwidths]
+    img_bytes = caps[0]
+    outs = [torch.empty(c, dtype=torch.uint8, device=dev) for c in caps]
     optrs = [o.data_ptr() for o in outs]
-    caps = [img_bytes] * ntr
 
     def step():
         sm.add_tracks_device(ids, ptrs, ns, srs, chs, exchange_max_sr=False)
@@ -209,7 +220,7 @@ def run_gpu(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sm.mt.set_global_max_sr(sr)
+    sm.mt.set_global_max_sr(max(srs))
     for _ in range(args.warmup):
         step()
     barrier()
@@ -238,12 +249,12 @@ def run_gpu(args, wl, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    audio_s_per_gpu = ntr * n / sr
+    audio_s_per_gpu = float(sum(m / r for m, r in zip(ns, srs)))
     value = audio_s_per_gpu * world / (ms_step * 1e-3)
 
     # ---- e2e: the host-buffer C ABI (pinned host PCM -> add_tracks_pcm -> get_spec_image_rgba -> host) ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and "srs" not in wl:
         e2e_tracks = ntr
         host_in = [torch.empty(x.shape, dtype=torch.float32).pin_memory() for x in tracks[:e2e_tracks]]
         for h, x in zip(host_in, tracks):
@@ -307,16 +318,19 @@ def run_gpu(args, wl, rank, world, local_rank):
     # parity spot check of what was timed (smoke-level; the real gate is tests/ -m gpu)
     sm.synchronize()
     rng = (sm.get_max_db(), sm.get_min_db())
+    shapes = {i: sm.mt.spec_shape(i) for i in ids}
     sm.close()
     if rank != 0:
         return None
     peak, peak_src = measured_peak()
-    alg_step = alg_bytes_per_audio_second(sr, ch) * audio_s_per_gpu  # per GPU per step
+    alg_step = float(sum(4 * ch * m + c for m, c in zip(ns, caps)))  # per GPU per step: PCM in + RGBA out
     k1 = float(np.median(k1_ms)); k3 = float(np.median(k3_ms))
-    T = n // st.hop_length + 1 if st.hop_length else n // 480 + 1
-    n_out = {"c5": 347, "c3": 128, "c1": 1025}[args.workload]
-    k1_own = (4 * ch * n + 4 * T * n_out) * ntr      # PCM read + dB written
-    k3_own = (4 * T * n_out + img_bytes) * ntr       # dB read + pixels written
+    db_bytes = 0
+    for i in ids:
+        T_i, n_out_i = shapes[i]
+        db_bytes += 4 * T_i * n_out_i
+    k1_own = float(sum(4 * ch * m for m in ns) + db_bytes)   # PCM read + dB written
+    k3_own = float(db_bytes + sum(caps))                      # dB read + pixels written
     roofline = {"bound": "hbm", "kernel": "stft_db_kernel (K1, fused frame/window/rFFT/|X|/mel/dB)",
                 "achieved": alg_step / (k1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_step / (k1 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
@@ -336,7 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c1"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c2", "c1"])
     ap.add_argument("--tracks", type=int, default=0, help="override tracks per GPU (profiling runs only)")
     ap.add_argument("--seconds", type=float, default=0, help="override track length (profiling runs only)")
     ap.add_argument("--no-e2e", action="store_true")

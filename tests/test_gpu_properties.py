@@ -85,3 +85,21 @@ def test_device_resident_batch_matches_host_path(msv):
     for o, wv in zip(outs, want):
         assert np.array_equal(o.cpu().numpy(), wv)
     sm.close()
+
+
+def test_bitwise_determinism(msv):
+    """Race detector of last resort (compute-sanitizer is closed on this pool): the analysis and render
+    kernels use named barriers and alias shared buffers, so two runs on the same input must agree bit for bit."""
+    sr = 48000
+    x = synth.base_clip(30 * sr, sr, 99)
+    outs = []
+    for _ in range(3):
+        mt = msv.MultiTrack()
+        mt.add_tracks_pcm([0, 1], [x, x[::-1].copy()], [sr, sr])
+        outs.append((mt.get_spec_db(0), mt.get_spec_db(1), mt.get_spec_image_rgba(0, 100.0, 500), mt.get_spec_image(1, 37.5, 123)))
+        mt.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    lin = [msv.melspectrogram_db(x[: 5 * sr], 4096, 256, 4096) for _ in range(2)]
+    assert np.array_equal(lin[0], lin[1])

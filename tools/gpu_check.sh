@@ -6,7 +6,7 @@ tail -3 gpurun_out/smoke.log
 timeout 1500 python -m pytest tests -m gpu -q -rA -s --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 grep -E "passed|failed|error" gpurun_out/pytest_gpu.log | tail -5
 grep -E "^FAILED" gpurun_out/pytest_gpu.log | head -20
-for wl in c5 c3 c1; do
+for wl in c5 c3 c2 c1; do
   extra=""; [ "$wl" != "c5" ] && extra="--no-cpu --no-e2e"
   [ -n "$BENCH_FAST" ] && extra="--no-cpu --no-e2e"
   timeout 900 python bench.py --workload $wl --steps 5 --warmup 3 $extra > gpurun_out/bench_$wl.log 2> gpurun_out/bench_$wl.err; echo "bench $wl exit $?" >> gpurun_out/bench_$wl.err
