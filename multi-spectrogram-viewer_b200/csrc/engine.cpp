@@ -69,6 +69,13 @@ FftPlan &DeviceCtx::plan(size_t n_fft)
         p->tw.alloc(h); p->split.alloc(h / 2 + 1);
         SGX_CUDA(cudaMemcpy(p->tw.p, tw.data(), sizeof(float2) * h, cudaMemcpyHostToDevice));
         SGX_CUDA(cudaMemcpy(p->split.p, sp.data(), sizeof(float2) * (h / 2 + 1), cudaMemcpyHostToDevice));
+        if (p->cfg.warp_per_frame) {
+            std::vector<float2> t2(1024), sf(1024);
+            make_warp_fft_tables(t2.data(), sf.data());
+            p->tw2.alloc(1024); p->split_full.alloc(1024);
+            SGX_CUDA(cudaMemcpy(p->tw2.p, t2.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+            SGX_CUDA(cudaMemcpy(p->split_full.p, sf.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+        }
     }
     it = plans_.emplace(n_fft, std::move(p)).first;
     return *it->second;
@@ -97,6 +104,7 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
         tt.mel_cnt.upload(mb.sched.data(), mb.sched.size(), s);
         tt.mel_w.upload(mb.w.data(), mb.w.size(), s);
         tt.mel_log2p = mb.log2_split;
+        tt.mel_nnz = (int)mb.w.size();
     }
     SGX_CUDA(cudaStreamSynchronize(s)); // host vectors die here
 }
@@ -327,17 +335,24 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         if (sec > max_sec_) { max_sec_ = sec; id_max_sec_ = ids[i]; }
     }
     // ---- update_specs (lib.rs:142-168): one K1 launch per FFT size -------------------------------------
-    std::map<size_t, std::vector<size_t>> by_fft;
-    for (size_t id : ids) by_fft[tracks_.at(id).n_fft].push_back(id);
+    // tracks that share an FFT size go into one launch; the warp-per-frame kernel stages window / mel tables
+    // once per CTA, so there a launch is additionally limited to tracks sharing those tables
+    std::map<std::pair<size_t, const TrackTables *>, std::vector<size_t>> by_fft;
+    for (size_t id : ids) {
+        const Track &t = tracks_.at(id);
+        const bool per_table = ctx_->plan(t.n_fft).cfg.warp_per_frame;
+        by_fft[std::make_pair(t.n_fft, per_table ? (const TrackTables *)t.tables : nullptr)].push_back(id);
+    }
     std::vector<StftTrack> descs;
     std::vector<size_t> desc_ids;
-    struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; };
+    struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; const TrackTables *tables = nullptr; };
     std::vector<Group> groups;
     for (auto &kv : by_fft) {
-        const StftConfig &cfg = ctx_->plan(kv.first).cfg;
+        const StftConfig &cfg = ctx_->plan(kv.first.first).cfg;
         int max_hop = 1;
         for (size_t id : kv.second) max_hop = std::max<int>(max_hop, (int)tracks_.at(id).hop);
-        Group g{kv.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop), 0};
+        Group g{kv.first.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop), 0};
+        g.tables = tracks_.at(kv.second.front()).tables;
         // a track id may appear twice in id_list; the last one wins, launch it once
         std::vector<size_t> uniq;
         for (size_t id : kv.second) if (std::find(uniq.begin(), uniq.end(), id) == uniq.end()) uniq.push_back(id);
@@ -364,6 +379,8 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
         L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
         L.tile_floats = g.tiling.tile_floats; L.tw = pl.tw.p; L.split = pl.split.p;
+        L.tw2 = pl.tw2.p; L.split_full = pl.split_full.p;
+        L.mel_nnz = g.tables ? g.tables->mel_nnz : 0; L.mel_rows = g.tables ? (int)g.tables->n_mel : 0;
         if (!pipelined) { SGX_CUDA(launch_stft(pl.cfg, L, stream_)); continue; }
         for (size_t k = 0; k < g.count; ++k) {
             const size_t di = g.first + k;
@@ -599,6 +616,7 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     L.n_tiles = (int)(((size_t)T + tl.frames_per_tile - 1) / tl.frames_per_tile);
     L.mode = mode; L.frames_per_tile = tl.frames_per_tile; L.staged = tl.staged; L.tile_floats = tl.tile_floats;
     L.tw = pl.tw.p; L.split = pl.split.p;
+    L.tw2 = pl.tw2.p; L.split_full = pl.split_full.p; L.mel_nnz = tt.mel_nnz; L.mel_rows = (int)tt.n_mel;
     SGX_CUDA(launch_stft(pl.cfg, L, s));
     SGX_CUDA(cudaMemcpyAsync(out, d_out.p, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     SGX_CUDA(cudaStreamSynchronize(s));

@@ -57,6 +57,7 @@ template <class T> struct DevBuf {
 struct FftPlan {
     StftConfig cfg;
     DevBuf<float2> tw, split;
+    DevBuf<float2> tw2, split_full; // warp-per-frame kernel (n_fft = 2048)
 };
 
 // everything that depends on (sr, win, n_fft, n_mel): the `windows` / `mel_fbs` caches, lib.rs:76-77
@@ -66,6 +67,7 @@ struct TrackTables {
     DevBuf<int> mel_lo, mel_cnt, mel_off;
     DevBuf<float> mel_w;
     int mel_log2p = 0;
+    int mel_nnz = 0;
 };
 
 struct AxisTableDev {

@@ -19,6 +19,7 @@ struct StftConfig {
     int min_ctas;          // resident CTAs per SM the kernel is compiled for
     size_t fft_smem;       // bytes of FFT exchange buffers
     bool generic;          // small-F fallback kernel (one CTA per frame)
+    bool warp_per_frame;   // n_fft = 2048: K1W, one warp per frame (persistent CTAs)
 };
 bool stft_config_for(size_t n_fft, StftConfig *cfg);
 size_t stft_max_dynamic_smem();
@@ -32,6 +33,8 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop);
 
 // FFT twiddle tables for one size (host vectors -> caller uploads).
 void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);
+void make_warp_fft_tables(float2 *tw2 /*[1024]*/, float2 *split_full /*[1024]*/);
+size_t stft_warp_smem_bytes(int nnz, int n_mel);
 
 // K2: global dB range (lib.rs:193-209)
 cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s);

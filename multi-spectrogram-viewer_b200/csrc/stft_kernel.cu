@@ -21,6 +21,7 @@
 //     coalesced stores, per-thread extrema are reduced to two atomics per CTA.
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -125,13 +126,17 @@ __device__ __forceinline__ float load_sample(const PcmView &pv, long long i)
 }
 
 // ---- in-register DFT of R points at re[BASE + i*STRIDE], natural order in and out ----------------
-// cos/sin(2 pi k / 16)
-__device__ constexpr float kC16[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f,
-                                      0.38268343236508977f, 0.0f, -0.38268343236508977f,
-                                      -0.70710678118654752f, -0.92387953251128674f};
-__device__ constexpr float kS16[8] = {0.0f, 0.38268343236508977f, 0.70710678118654752f,
-                                      0.92387953251128674f, 1.0f, 0.92387953251128674f,
-                                      0.70710678118654752f, 0.38268343236508977f};
+// cos/sin(2 pi k / 32), k < 16
+__device__ constexpr float kC32[16] = {
+    1.0f, 0.98078528040323044f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+    0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f, -0.19509032201612825f,
+    -0.38268343236508977f, -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+    -0.92387953251128674f, -0.98078528040323044f};
+__device__ constexpr float kS32[16] = {
+    0.0f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f, 0.70710678118654752f,
+    0.83146961230254524f, 0.92387953251128674f, 0.98078528040323044f, 1.0f, 0.98078528040323044f,
+    0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+    0.38268343236508977f, 0.19509032201612825f};
 
 template <int R, int BASE, int STRIDE, int PTS, int V>
 __device__ __forceinline__ void dft_inplace(float (&re)[PTS][V], float (&im)[PTS][V])
@@ -151,14 +156,14 @@ __device__ __forceinline__ void dft_inplace(float (&re)[PTS][V], float (&im)[PTS
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
             const int e = BASE + 2 * k * STRIDE, o = BASE + (2 * k + 1) * STRIDE;
-            const int widx = k * (16 / R); // exp(-2 pi i k / R) = kC16[widx] - i kS16[widx]
+            const int widx = k * (32 / R); // exp(-2 pi i k / R) = kC32[widx] - i kS32[widx]
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 float pr, pi;
                 if (widx == 0) { pr = re[o][v]; pi = im[o][v]; }
-                else if (widx == 4) { pr = im[o][v]; pi = -re[o][v]; }
+                else if (widx == 8) { pr = im[o][v]; pi = -re[o][v]; }
                 else {
-                    const float c = kC16[widx], s = kS16[widx];
+                    const float c = kC32[widx], s = kS32[widx];
                     pr = re[o][v] * c + im[o][v] * s;
                     pi = im[o][v] * c - re[o][v] * s;
                 }
@@ -679,6 +684,212 @@ stft_db_kernel(const StftLaunch L)
     }
 }
 
+// =====================================================================================================
+// K1W -- warp-per-frame variant of the fused analysis kernel for n_fft = 2048 (h = 1024 = 32 x 32).
+//
+// One warp owns one frame: lane m2 first holds the 32 points z[32 m1 + m2] and runs a 32-point DFT in
+// registers, the twiddle W_1024^(m2 k1) is applied, one transpose through a private 8.25 KB shared
+// buffer re-distributes the data so that lane k1 holds A[k1][m2] for all m2, and a second in-register
+// 32-point DFT yields Z[k1 + 32 k2].  The conjugate partner of bin k1 + 32 k2 lives in lane 32 - k1,
+// register 31 - k2, so the real-FFT split is one pair of warp shuffles per bin.  No block barrier
+// exists on the frame path (16 independent warps per SM hide each other's latencies) and the spectrum
+// crosses shared memory once instead of three times.  Frames are read straight from global memory
+// with coalesced 64-bit loads; the 4x overlap between neighbouring frames -- which neighbouring warps
+// of the same CTA process at the same time -- is served by L1.  Window, twiddle, split and mel tables
+// are staged in shared memory once per (persistent) CTA.
+// =====================================================================================================
+constexpr int kWH = 1024;             // complex points
+constexpr int kWWarps = 16;
+constexpr int kWThreads = kWWarps * 32;
+constexpr int kWXchg = 32 * 33;       // float2 elements of one warp's transpose buffer (pitch 33)
+
+__host__ __device__ inline size_t k1w_smem_bytes(int nnz, int n_mel)
+{
+    return (size_t)kWWarps * kWXchg * sizeof(float2) + 2048 * sizeof(float) + 2 * kWH * sizeof(float2) +
+           (size_t)(((nnz + 3) & ~3) + 64) * sizeof(float) + (size_t)n_mel * sizeof(int4) + 16;
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) stft_warp_kernel(const StftLaunch L, int nnz, int n_mel_tab)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *xall = reinterpret_cast<float2 *>(smem_raw);
+    float *win_s = reinterpret_cast<float *>(xall + kWWarps * kWXchg);
+    float2 *tw2_s = reinterpret_cast<float2 *>(win_s + 2048);
+    float2 *spl_s = tw2_s + kWH;
+    float *wts_s = reinterpret_cast<float *>(spl_s + kWH);
+    int4 *meta_s = reinterpret_cast<int4 *>(wts_s + ((nnz + 3) & ~3) + 64);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mode = L.mode;
+    // ---- tables (all tracks of a launch share them; the host groups launches accordingly) --------------
+    {
+        const StftTrack *__restrict__ t0 = L.tracks;
+        for (int i = tid; i < 2048; i += kWThreads) win_s[i] = __ldg(t0->win_f + i);
+        for (int i = tid; i < kWH; i += kWThreads) { tw2_s[i] = __ldg(L.tw2 + i); spl_s[i] = __ldg(L.split_full + i); }
+        if (mode == MODE_MEL_DB) {
+            for (int i = tid; i < ((nnz + 3) & ~3) + 64; i += kWThreads) wts_s[i] = i < nnz ? __ldg(t0->mel_w + i) : 0.0f;
+            const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(t0->mel_lo);
+            for (int i = tid; i < n_mel_tab; i += kWThreads) meta_s[i] = __ldg(meta + i);
+        }
+    }
+    __syncthreads();
+
+    float2 *xb = xall + warp * kWXchg;
+    float *magbuf = reinterpret_cast<float *>(xb); // [1025] magnitudes of the current frame (mel mode)
+    const float2 *win2 = reinterpret_cast<const float2 *>(win_s);
+
+    int cur = 0; // current track (frames are enumerated track after track)
+    float vmax = -INFINITY, vmin = INFINITY;
+    auto flush_range = [&](const StftTrack *td) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
+        }
+        if (lane == 0 && td->range_slot != nullptr && vmax >= vmin) {
+            atomicMax(td->range_slot, enc_ordered(vmax));
+            atomicMin(td->range_slot + 1, enc_ordered(vmin));
+        }
+        vmax = -INFINITY; vmin = INFINITY;
+    };
+
+    for (int g = blockIdx.x * kWWarps + warp; g < L.n_tiles; g += gridDim.x * kWWarps) {
+        // ---- which track / frame (tile_begin holds the frame prefix: one "tile" per frame) ----------------
+        int nxt = cur;
+        while (nxt + 1 < L.n_tracks && L.tracks[nxt + 1].tile_begin <= g) ++nxt;
+        if (nxt != cur) { flush_range(L.tracks + cur); cur = nxt; }
+        const StftTrack *__restrict__ td = L.tracks + cur;
+        const PcmView pv{td->pcm, td->n, td->ch, td->fmt};
+        const int t = g - td->tile_begin;
+        const long long S0 = (long long)t * td->hop - td->win / 2 - td->pad_l;
+        float *__restrict__ out = td->out;
+        const int n_out = td->n_out;
+
+        float re[32][1], im[32][1];
+        // ---- A: windowed samples, z[32 m1 + lane] = (g[2m], g[2m+1]) ------------------------------------------
+        const bool interior = pv.ch == 1 && pv.fmt == PCM_F32 && S0 >= 0 && S0 + 2 * kWH <= pv.n;
+        if (interior && ((S0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(pv.pcm) & 7) == 0)) {
+            const float2 *__restrict__ p = reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(pv.pcm) + S0) + lane;
+#pragma unroll
+            for (int m1 = 0; m1 < 32; ++m1) {
+                const float2 x = __ldg(p + 32 * m1);
+                const float2 w = win2[32 * m1 + lane];
+                re[m1][0] = x.x * w.x; im[m1][0] = x.y * w.y;
+            }
+        } else if (interior) {
+            const float *__restrict__ p = reinterpret_cast<const float *>(pv.pcm) + S0 + 2 * lane;
+#pragma unroll
+            for (int m1 = 0; m1 < 32; ++m1) {
+                const float2 w = win2[32 * m1 + lane];
+                re[m1][0] = __ldg(p + 64 * m1) * w.x; im[m1][0] = __ldg(p + 64 * m1 + 1) * w.y;
+            }
+        } else {
+#pragma unroll
+            for (int m1 = 0; m1 < 32; ++m1) {
+                const float2 w = win2[32 * m1 + lane];
+                const long long i = S0 + 64 * m1 + 2 * lane;
+                re[m1][0] = load_sample(pv, i) * w.x; im[m1][0] = load_sample(pv, i + 1) * w.y;
+            }
+        }
+        // ---- B: 32-point DFT over m1, twiddle W_1024^(lane k1) ----------------------------------------------------
+        dft_inplace<32, 0, 1, 32, 1>(re, im);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+            const float2 w = tw2_s[k1 * 32 + lane];
+            const float xr = re[k1][0], xi = im[k1][0];
+            re[k1][0] = xr * w.x - xi * w.y; im[k1][0] = xr * w.y + xi * w.x;
+        }
+        // ---- C: transpose through the warp's buffer (pitch 33 float2: both sides conflict free) -----------------
+        __syncwarp(); // previous frame's magnitudes are consumed
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) xb[k1 * 33 + lane] = make_float2(re[k1][0], im[k1][0]);
+        __syncwarp();
+#pragma unroll
+        for (int m2 = 0; m2 < 32; ++m2) { const float2 v = xb[lane * 33 + m2]; re[m2][0] = v.x; im[m2][0] = v.y; }
+        __syncwarp();
+        // ---- D: 32-point DFT over m2 -> Z[lane + 32 k2] in register k2 -----------------------------------------------
+        dft_inplace<32, 0, 1, 32, 1>(re, im);
+        // ---- E: real-FFT split (realfft.rs:140-157); partner bin lives in lane 32-lane, register 31-k2 ------------
+        const int pl = (32 - lane) & 31;
+        const bool l0 = lane == 0;
+        const size_t row = (size_t)t * (kWH + 1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            // lane 0 pairs k = 32 j with 32 (32 - j): it offers register (32 - j) & 31 instead of 31 - j
+            const float sr = l0 ? re[(32 - j) & 31][0] : re[31 - j][0];
+            const float si = l0 ? im[(32 - j) & 31][0] : im[31 - j][0];
+            const float br = __shfl_sync(0xffffffffu, sr, pl), bi = __shfl_sync(0xffffffffu, si, pl);
+            const float ar = re[j][0], ai = im[j][0];
+            const int k = lane + 32 * j;
+            const float2 cs = spl_s[k]; // (cos, sin)(k pi / h)
+            const float sumr = ar + br, difr = ar - br, sumi = ai + bi, difi = ai - bi;
+            const float xr = 0.5f * (sumr + fmaf(cs.x, sumi, -cs.y * difr));
+            const float xi = 0.5f * (difi - fmaf(cs.y, sumi, cs.x * difr));
+            if (mode == MODE_COMPLEX) {
+                reinterpret_cast<float2 *>(out)[row + k] = make_float2(xr, xi);
+            } else {
+                const float mg = sqrt_approx(fmaf(xr, xr, xi * xi)); // lib.rs:124
+                if (mode == MODE_MEL_DB) magbuf[k] = mg;
+                else {
+                    float y = mg;
+                    if (mode == MODE_LIN_DB) { y = amp_to_db_dev(y); vmax = fmaxf(vmax, y); vmin = fminf(vmin, y); }
+                    out[row + k] = y;
+                }
+            }
+        }
+        if (l0) { // Nyquist bin: Z[0].re - Z[0].im (realfft.rs:157)
+            const float xr = re[0][0] - im[0][0];
+            if (mode == MODE_COMPLEX) reinterpret_cast<float2 *>(out)[row + kWH] = make_float2(xr, 0.0f);
+            else {
+                const float mg = fabsf(xr);
+                if (mode == MODE_MEL_DB) magbuf[kWH] = mg;
+                else {
+                    float y = mg;
+                    if (mode == MODE_LIN_DB) { y = amp_to_db_dev(y); vmax = fmaxf(vmax, y); vmin = fminf(vmin, y); }
+                    out[row + kWH] = y;
+                }
+            }
+        }
+        // ---- F: banded mel projection + dB (lanes <-> filters) --------------------------------------------------------
+        if (mode == MODE_MEL_DB) {
+            __syncwarp();
+            const int lg = td->mel_log2p, P = 1 << lg;
+            const int items = n_out << lg;
+            for (int w0 = 0; w0 < items; w0 += 32) {
+                const int wi = w0 + lane;
+                const int m = wi >> lg, plm = wi & (P - 1);
+                const bool valid = m < n_out;
+                int4 mt = make_int4(0, 0, 0, 0);
+                if (valid) mt = meta_s[m];
+                const int nj = mt.y > plm ? (mt.y - plm + P - 1) >> lg : 0;
+                const int njmax = __reduce_max_sync(0xffffffffu, nj);
+                const float *wp = wts_s + mt.z + plm;
+                const float *mp = magbuf + mt.x + plm;
+                float acc = 0.0f;
+                // loads are unconditional (the tables are zero-padded and the buffer is larger than the
+                // spectrum); taps past this lane's band are zeroed by the select
+                if (lg == 0) {
+#pragma unroll 4
+                    for (int jj = 0; jj < njmax; ++jj) acc = fmaf(mp[jj], jj < nj ? wp[jj] : 0.0f, acc);
+                } else {
+#pragma unroll 2
+                    for (int jj = 0; jj < njmax; ++jj) {
+                        const bool on = jj < nj;
+                        acc = fmaf(on ? mp[jj << lg] : 0.0f, on ? wp[jj << lg] : 0.0f, acc);
+                    }
+                }
+                for (int s = P >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+                if (valid && plm == 0) {
+                    const float y = amp_to_db_dev(acc);
+                    vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+                    out[(size_t)t * n_out + m] = y;
+                }
+            }
+        }
+    }
+    if (mode == MODE_LIN_DB || mode == MODE_MEL_DB) flush_range(L.tracks + cur);
+}
+
 // ---- small-F fallback: one CTA per frame, radix-2 Stockham, any power-of-two F >= 2 --------------------
 // Covers the reference's known-answer shapes (n_fft = 4, 256) and anything below the tuned sizes.
 __global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, int h)
@@ -835,14 +1046,30 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
     }
     SGX_K1_TABLE(X)
 #undef X
+    // n_fft = 2048: SGX_K1W=1 selects the warp-per-frame kernel instead of the block kernel above.  Measured on
+    // B200 (C5): 65 % issue-slot use vs 51 %, but 1.25x the instructions (no sharing of index math, tables and
+    // mel taps across 4 frames) -> 9.9 ms vs 9.4 ms; kept as an evaluated alternative, off by default.
+    static const bool k1w_on = getenv("SGX_K1W") && atoi(getenv("SGX_K1W")) == 1;
+    cfg->warp_per_frame = false;
+    if (h == kWH && k1w_on && want_pts == 0) {
+        cfg->warp_per_frame = true; cfg->generic = false;
+        cfg->pts = 32; cfg->vec = 1; cfg->groups = kWWarps; cfg->threads = kWThreads; cfg->min_ctas = 1;
+        cfg->fft_smem = 0;
+    }
     return true;
 }
+
+size_t stft_warp_smem_bytes(int nnz, int n_mel) { return k1w_smem_bytes(nnz, n_mel); }
 
 size_t stft_max_dynamic_smem() { return 227 * 1024; }
 
 StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop)
 {
     StftTiling t{};
+    if (cfg.warp_per_frame) { // one "tile" per frame; nothing is staged per tile
+        t.frames_per_tile = 1; t.staged = 0; t.tile_floats = 0; t.smem_bytes = 0;
+        return t;
+    }
     if (cfg.generic) {
         t.frames_per_tile = 1; t.staged = 0; t.tile_floats = 0;
         t.smem_bytes = cfg.fft_smem;
@@ -876,6 +1103,20 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop)
     return t;
 }
 
+void make_warp_fft_tables(float2 *tw2 /*[32*32]*/, float2 *split_full /*[1024]*/)
+{
+    const double pi = 3.14159265358979323846264338327950288;
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int lane = 0; lane < 32; ++lane) {
+            const double a = -2.0 * pi * (double)(k1 * lane) / (double)kWH; // W_1024^(lane k1)
+            tw2[k1 * 32 + lane] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int k = 0; k < kWH; ++k) {
+        const double a = pi * (double)k / (double)kWH;
+        split_full[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
 void make_fft_tables(int h, float2 *tw, float2 *split)
 {
     const double pi = 3.14159265358979323846264338327950288;
@@ -892,6 +1133,26 @@ void make_fft_tables(int h, float2 *tw, float2 *split)
 cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t stream)
 {
     if (L.n_tiles <= 0) return cudaSuccess;
+    if (cfg.warp_per_frame) {
+        const size_t smem = k1w_smem_bytes(L.mel_nnz, L.mel_rows);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(stft_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (sms <= 0) sms = 148;
+        }
+        const int grid = std::min(sms, (L.n_tiles + kWWarps - 1) / kWWarps);
+        stft_warp_kernel<<<grid, kWThreads, smem, stream>>>(L, L.mel_nnz, L.mel_rows);
+        count_launch();
+        return cudaGetLastError();
+    }
     const size_t smem = cfg.generic ? cfg.fft_smem
                                     : 16 + (size_t)L.tile_floats * sizeof(float) + cfg.fft_smem;
     if (cfg.generic) {

@@ -103,3 +103,35 @@ def test_bitwise_determinism(msv):
             assert np.array_equal(a, b)
     lin = [msv.melspectrogram_db(x[: 5 * sr], 4096, 256, 4096) for _ in range(2)]
     assert np.array_equal(lin[0], lin[1])
+
+
+def test_warp_per_frame_variant_parity(orc):
+    """The alternative n_fft = 2048 kernel (SGX_K1W=1, one warp per frame) must meet the same tolerances;
+    it is selected per process, so it runs in a child interpreter."""
+    import subprocess
+    import sys
+    import os
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import msv_b200 as msv, oracle_binding, synth
+from parity import assert_db_close
+orc = oracle_binding.load()
+x = synth.base_clip(3 * 48000 + 77, 48000, 5)
+ref = orc.perform_stft(x, 1920, 480, 2048)
+got = msv.perform_stft(x, 1920, 480, 2048)
+peak = np.abs(ref).max(axis=1, keepdims=True)
+assert (np.abs(got - ref) / peak).max() <= 1e-4
+fb = msv.calc_mel_fb_default(48000, 2048)
+assert_db_close(msv.melspectrogram_db(x, 1920, 480, 2048, None, fb), orc.calc_spec(x, 1920, 480, 2048, None, fb), "K1W mel")
+assert_db_close(msv.melspectrogram_db(x, 2048, 512, 2048), orc.calc_spec(x, 2048, 512, 2048), "K1W linear")
+y = synth.base_clip(2 * 44100, 44100, 6)  # odd hop 441: unaligned frame starts
+fb = msv.calc_mel_fb_default(44100, 2048)
+assert_db_close(msv.melspectrogram_db(y, 1764, 441, 2048, None, fb), orc.calc_spec(y, 1764, 441, 2048, None, fb), "K1W 44.1k")
+print("K1W OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SGX_K1W="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "K1W OK" in r.stdout, r.stdout + r.stderr
