@@ -331,9 +331,17 @@ def run_gpu(args, wl, rank, world, local_rank):
         db_bytes += 4 * T_i * n_out_i
     k1_own = float(sum(4 * ch * m for m in ns) + db_bytes)   # PCM read + dB written
     k3_own = float(db_bytes + sum(caps))                      # dB read + pixels written
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get(args.workload)
+        if tr and not (args.tracks or args.seconds):
+            traffic = tr["k1_stft_db_bytes"] / tr["audio_seconds_in_capture"] * audio_s_per_gpu
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": "stft_db_kernel (K1, fused frame/window/rFFT/|X|/mel/dB)",
                 "achieved": alg_step / (k1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_step / (k1 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": alg_step / (k1 * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_step, "kernel_ms": k1,
                 "note": "algorithmic bytes = SURVEY 8(d) per-unit figure (f32 PCM in + RGBA out) x audio seconds per launch"}
     step_roof = {"achieved": alg_step / (ms_step * 1e-3) / 1e9, "frac": alg_step / (ms_step * 1e-3) / 1e9 / peak,
