@@ -240,8 +240,9 @@ def run_gpu(args, wl, rank, world, local_rank):
     clk = clocks.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     # per-kernel durations (CUDA events on the engine's stream around K1 / K3), a few extra steps
-    for _ in range(min(3, args.steps)):
-        step()
+    for _ in range(3):
+        for _ in range(3):  # back-to-back steps: the events of the last one are read in steady state
+            step()
         a, r = sm.mt.stage_times()
         k1_ms.append(a); k3_ms.append(r)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -345,7 +346,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                 "algorithmic_bytes_per_launch": alg_step, "kernel_ms": k1,
                 "note": "algorithmic bytes = SURVEY 8(d) per-unit figure (f32 PCM in + RGBA out) x audio seconds per launch"}
     step_roof = {"achieved": alg_step / (ms_step * 1e-3) / 1e9, "frac": alg_step / (ms_step * 1e-3) / 1e9 / peak,
-                 "k1_ms": k1, "k3_ms": k3, "step_ms": ms_step,
+                 "k1_ms": k1, "k3_ms": k3, "step_ms": ms_step, "k1_ms_samples": k1_ms, "k3_ms_samples": k3_ms,
                  "k1_own_bytes_gbs": k1_own / (k1 * 1e-3) / 1e9, "k3_own_bytes_gbs": k3_own / (k3 * 1e-3) / 1e9,
                  "note": "whole step (K1+K2+K3) against the same algorithmic bytes; *_own_bytes = each kernel's own minimal HBM traffic incl. the dB intermediate"}
     return {"value": value, "ms_per_step": ms_step, "roofline": roofline, "roofline_step": step_roof, "e2e": e2e,

@@ -227,7 +227,13 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
                 w[6] = make_float2(w[3].x * w[3].x - w[3].y * w[3].y, 2.0f * w[3].x * w[3].y);
                 w[7] = make_float2(w[4].x * w[3].x - w[4].y * w[3].y, w[4].x * w[3].y + w[4].y * w[3].x);
             }
-            static_assert(R <= 8, "twiddle powers are written out for radix <= 8");
+            if constexpr (R >= 16) {
+                auto cm = [](float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); };
+                w[8] = make_float2(w[4].x * w[4].x - w[4].y * w[4].y, 2.0f * w[4].x * w[4].y);
+                w[9] = cm(w[8], w[1]); w[10] = cm(w[8], w[2]); w[11] = cm(w[8], w[3]); w[12] = cm(w[8], w[4]);
+                w[13] = cm(w[8], w[5]); w[14] = cm(w[8], w[6]); w[15] = cm(w[8], w[7]);
+            }
+            static_assert(R <= 16, "twiddle powers are written out for radix <= 16");
 #pragma unroll
             for (int r = 1; r < R; ++r) {
 #pragma unroll
@@ -1005,21 +1011,19 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 
 } // namespace
 
-// FFT size -> kernel instantiations (LOG2H, PTS, V, G).  The first entry of a size is the default; the
-// others are selectable with SGX_K1_VARIANT="pts,v,g" (tuning experiments).
+// FFT size -> kernel instantiations (LOG2H, PTS, V, G, resident CTAs).  The first entry of a size is the
+// default; the others are selectable with SGX_K1_VARIANT="pts,v,g" (tuning experiments).  Measured on B200 for
+// h = 1024 (8 tracks x 10 min, K1 ms): (8,4,2) 2.35 | (8,2,2) 3.09 | (8,2,4) 3.39 | (4,4,1) 2.80 | (4,4,2) 2.85 |
+// (16,2,4) 3.16 | (16,2,2) 3.38 -- sharing index math, twiddles and mel taps across V = 4 frames outweighs the
+// higher occupancy of the V = 2 variants and the fewer exchanges of radix 16.
 #define SGX_K1_TABLE(X) \
     X(8, 8, 4, 8, 2)    \
     X(9, 8, 4, 4, 2)    \
     X(10, 8, 4, 2, 2)   \
     X(10, 8, 2, 2, 3)   \
-    X(10, 8, 2, 4, 2)   \
     X(10, 4, 4, 1, 4)   \
-    X(10, 4, 4, 2, 2)   \
     X(11, 8, 4, 1, 2)   \
-    X(11, 8, 2, 1, 3)   \
-    X(11, 8, 2, 2, 1)   \
     X(12, 8, 4, 1, 1)   \
-    X(12, 8, 2, 1, 1)   \
     X(13, 8, 2, 1, 1)
 
 bool stft_config_for(size_t n_fft, StftConfig *cfg)
