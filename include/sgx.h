@@ -189,6 +189,22 @@ SGX_API int sgx_mt_get_image_width(sgx_multitrack *mt, size_t id, float px_per_s
  * synchronises. */
 SGX_API int sgx_mt_range_device_ptr(sgx_multitrack *mt, float **d_max_negmin);
 SGX_API int sgx_mt_commit_range_device(sgx_multitrack *mt);
+/* Time-sharding ONE long track over several GPUs.  Every GPU owns a strip of output columns:
+ * sgx_slice_plan tells which frames that strip needs (its Lanczos taps) and which samples those frames read
+ * (with the reflection at the true ends of the track); the driver uploads just those samples, registers them
+ * with sgx_mt_add_track_slice_device (deferred like sgx_mt_add_tracks_pcm_device: all-reduce the range, then
+ * sgx_mt_commit_range_device) and renders the strip with sgx_mt_get_spec_image_slice_device into a
+ * [nheight][ox_count][channels] buffer.  Strips of all GPUs side by side are bit-identical to the image of
+ * the whole track. */
+SGX_API int sgx_slice_plan(size_t n_total, uint32_t sr, const sgx_settings *settings, float px_per_sec,
+                           uint32_t ox_begin, uint32_t ox_count, size_t *frame_begin, size_t *frame_count,
+                           size_t *sample_begin, size_t *sample_count);
+SGX_API int sgx_mt_add_track_slice_device(sgx_multitrack *mt, size_t id, const float *d_pcm,
+                                          size_t chunk_offset, size_t chunk_len, size_t n_total, uint32_t sr,
+                                          uint32_t channels, size_t frame_begin, size_t frame_count);
+SGX_API int sgx_mt_get_spec_image_slice_device(sgx_multitrack *mt, size_t id, float px_per_sec,
+                                               uint32_t nheight, int channels, uint32_t ox_begin,
+                                               uint32_t ox_count, uint8_t *d_out, size_t cap, size_t *written);
 /* max sample rate across ALL shards (lib.rs:220-224 is metadata-only; the driver max-reduces it
  * on the host before the first render).  0 = use the local maximum. */
 SGX_API int sgx_mt_set_global_max_sr(sgx_multitrack *mt, uint32_t max_sr);

@@ -100,6 +100,9 @@ PROTOTYPES = {
     "sgx_mt_range_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
     "sgx_mt_commit_range_device": (C.c_int, [_vp]),
     "sgx_mt_set_global_max_sr": (C.c_int, [_vp, _u32]),
+    "sgx_slice_plan": (C.c_int, [_sz, _u32, C.POINTER(Settings), _f, _u32, _u32, _psz, _psz, _psz, _psz]),
+    "sgx_mt_add_track_slice_device": (C.c_int, [_vp, _sz, _vp, _sz, _sz, _sz, _u32, _u32, _sz, _sz]),
+    "sgx_mt_get_spec_image_slice_device": (C.c_int, [_vp, _sz, _f, _u32, C.c_int, _u32, _u32, _vp, _sz, _psz]),
     "sgx_mt_set_profiling": (C.c_int, [_vp, C.c_int]),
     "sgx_mt_get_stage_times": (C.c_int, [_vp, _pf, _pf]),
     "sgx_mt_synchronize": (C.c_int, [_vp, _pi]),
@@ -293,6 +296,20 @@ def open_audio_file(path: str):
     return buf.T, sr.value  # the [ch, n] view over interleaved memory of audio.rs:33-35
 
 
+def calc_nwidth_like(px_per_sec: float, n: int, sr: int) -> int:
+    """nwidth of lib.rs:296: (px_per_sec * len as f32 / sr as f32) as u32, in f32 arithmetic."""
+    v = np.float32(px_per_sec) * np.float32(n) / np.float32(sr)
+    return int(v) if v > 0 else 0
+
+
+def slice_plan(n_total: int, sr: int, px_per_sec: float, ox_begin: int, ox_count: int, settings: Optional[Settings] = None):
+    """Frames and samples a strip of output columns needs -> (frame_begin, frame_count, sample_begin, sample_count)."""
+    fb, fc, sb, sc = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _check(_lib.sgx_slice_plan(n_total, sr, C.byref(settings) if settings is not None else None, px_per_sec, ox_begin, ox_count,
+                               C.byref(fb), C.byref(fc), C.byref(sb), C.byref(sc)))
+    return fb.value, fc.value, sb.value, sc.value
+
+
 def get_colormap() -> np.ndarray:
     """get_colormap (lib.rs:473-480): 30 bytes."""
     out = np.empty(30, np.uint8)
@@ -373,6 +390,21 @@ class MultiTrack:
             for i in id_list:
                 self._keep[i] = keepalive
         return bool(ch.value) if sync else None
+
+    def add_track_slice_device(self, id: int, ptr: int, chunk_offset: int, chunk_len: int, n_total: int, sr: int, channels: int,
+                               frame_begin: int, frame_count: int, keepalive=None) -> None:
+        """One time slice of a long track (device PCM, deferred; see sgx_mt_add_track_slice_device)."""
+        _check(_lib.sgx_mt_add_track_slice_device(self._h, id, _vp(int(ptr)), chunk_offset, chunk_len, n_total, sr, channels,
+                                                  frame_begin, frame_count))
+        if keepalive is not None:
+            self._keep[id] = keepalive
+
+    def render_slice_device(self, id: int, px_per_sec: float, nheight: int, channels: int, ox_begin: int, ox_count: int,
+                            out_ptr: int, cap: int) -> int:
+        wr = C.c_size_t()
+        _check(_lib.sgx_mt_get_spec_image_slice_device(self._h, id, px_per_sec, nheight, channels, ox_begin, ox_count,
+                                                       _vp(int(out_ptr)), cap, C.byref(wr)))
+        return wr.value
 
     def remove_track(self, id: int, sync: bool = True) -> Optional[bool]:
         ch = C.c_int()

@@ -150,6 +150,64 @@ int sgx_mt_add_tracks(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, c
     });
 }
 
+int sgx_mt_add_track_slice_device(sgx_multitrack *mt, size_t id, const float *d_pcm, size_t chunk_offset,
+                                  size_t chunk_len, size_t n_total, uint32_t sr, uint32_t channels,
+                                  size_t frame_begin, size_t frame_count)
+{
+    return guarded([&] {
+        REQUIRE(mt && d_pcm, "NULL argument");
+        REQUIRE(n_total > 0 && chunk_len > 0, "empty slice");
+        std::vector<size_t> ids{id};
+        std::vector<PcmSource> srcs(1);
+        srcs[0] = PcmSource{d_pcm, PCM_F32, chunk_len, sr, channels, true, std::string()};
+        srcs[0].n_total = n_total; srcs[0].origin = chunk_offset;
+        srcs[0].frame_begin = frame_begin; srcs[0].frame_count = frame_count;
+        mt->impl.add_tracks(ids, srcs, false);
+    });
+}
+
+int sgx_mt_get_spec_image_slice_device(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t nheight,
+                                       int channels, uint32_t ox_begin, uint32_t ox_count, uint8_t *d_out,
+                                       size_t cap, size_t *written)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        uint8_t *outs[1] = {d_out};
+        size_t caps[1] = {cap};
+        std::vector<size_t> ids{id};
+        mt->impl.render(ids, px_per_sec, nheight, channels, d_out ? outs : nullptr, caps, written, &ox_begin, &ox_count);
+    });
+}
+
+int sgx_slice_plan(size_t n_total, uint32_t sr, const sgx_settings *settings, float px_per_sec, uint32_t ox_begin,
+                   uint32_t ox_count, size_t *frame_begin, size_t *frame_count, size_t *sample_begin,
+                   size_t *sample_count)
+{
+    return guarded([&] {
+        REQUIRE(frame_begin && frame_count && sample_begin && sample_count, "NULL argument");
+        size_t win = 0, hop = 0, n_fft = 0;
+        if (sgx_track_params(sr, settings, &win, &hop, &n_fft) != SGX_OK) throw Error(SGX_ERR_BAD_ARG, sgx_last_error());
+        REQUIRE(n_fft >= win, "win_length > n_fft");
+        const long T = stft_num_frames(n_total, win, hop);
+        if (T <= 0) throw Error(SGX_ERR_BAD_ARG, "track shorter than one window");
+        const uint32_t nwidth = calc_nwidth(px_per_sec, n_total, sr);
+        REQUIRE(ox_count > 0 && ox_begin < nwidth && ox_count <= nwidth - ox_begin, "column window outside the image");
+        uint32_t l0, r0, l1, r1;
+        lanczos3_span((uint32_t)T, nwidth, ox_begin, &l0, &r0);
+        lanczos3_span((uint32_t)T, nwidth, ox_begin + ox_count - 1, &l1, &r1);
+        *frame_begin = l0; *frame_count = r1 - l0;
+        // samples those frames read (zero-padded FFT frame, a few samples of slack so that the aligned bulk
+        // copies of K1 stay inside the chunk), extended by what the reflection at either end of the track needs
+        const long long n = (long long)n_total, pad_l = (long long)(n_fft - win) / 2;
+        long long lo = (long long)l0 * (long long)hop - (long long)(win / 2) - pad_l - 8;
+        long long hi = (long long)(r1 - 1) * (long long)hop - (long long)(win / 2) - pad_l + (long long)n_fft + 8;
+        if (lo < 0) hi = std::max(hi, -lo + 1);
+        if (hi > n) lo = std::min(lo, 2 * (n - 1) - (hi - 1));
+        lo = std::max(0LL, std::min(lo, n)); hi = std::max(0LL, std::min(hi, n));
+        *sample_begin = (size_t)lo; *sample_count = (size_t)(hi - lo);
+    });
+}
+
 int sgx_mt_remove_track(sgx_multitrack *mt, size_t id, int *changed)
 {
     return guarded([&] {

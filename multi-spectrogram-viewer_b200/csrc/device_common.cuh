@@ -18,11 +18,14 @@ enum PcmFormat : int { PCM_F32 = 0, PCM_I16 = 1 };
 // One track of a K1 launch (device-resident array of these).
 struct StftTrack {
     const void *pcm;       // interleaved [n][ch], f32 or i16 (audio.rs:16-19 scale applied on load)
-    long long n;           // samples per channel
+    long long n;           // samples per channel of the WHOLE track (reflection happens at 0 and n-1)
+    long long origin;      // global sample index of pcm[0]  (0 unless the handle holds a time slice)
+    long long avail;       // samples per channel present at `pcm` (n unless a time slice)
+    int frame0;            // global index of the first frame this descriptor produces (row 0 of `out`)
     int ch;
     int fmt;               // PcmFormat
     int win, hop, pad_l;   // W, H, (F-W)/2                              lib.rs:400
-    int n_frames;          // T                                           lib.rs:435
+    int n_frames;          // frames to produce (T of lib.rs:435 unless a time slice)
     const float *win_f;    // [F]: window centred in the FFT frame, zeros outside (lib.rs:377-384)
     float *out;            // see StftMode
     int n_out;             // h+1 or n_mel
@@ -79,8 +82,10 @@ __device__ __forceinline__ float amp_to_db_dev(float x)
 
 // One track of a K3 launch.
 struct RenderTrack {
-    const float *src;      // dB [T][n_out]  (from_db)  or grey [height][width]
-    int width;             // T
+    const float *src;      // dB [rows][n_out]  (from_db)  or grey [height][width]
+    int width;             // T of the whole track
+    int frame0, src_frames; // from_db: src row r holds global frame frame0 + r, src_frames rows exist
+    int ox_begin, ox_count; // output columns rendered by this launch; `out` is [nheight][ox_count]
     int n_out;             // rows of the dB array (from_db)
     int height;            // grey height = round(n_out * up_ratio)     display.rs:45
     int nwidth, nheight;

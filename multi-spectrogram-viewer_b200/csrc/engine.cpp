@@ -111,10 +111,11 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
 
 static StftTrack make_desc(const void *d_pcm, int fmt, size_t n, uint32_t ch, size_t win, size_t hop,
                            size_t n_fft, size_t T, const TrackTables &tt, float *out, size_t n_out,
-                           unsigned *slot)
+                           unsigned *slot, size_t origin = 0, size_t avail = (size_t)-1, size_t frame0 = 0)
 {
     StftTrack d{};
     d.pcm = d_pcm; d.n = (long long)n; d.ch = (int)ch; d.fmt = fmt;
+    d.origin = (long long)origin; d.avail = (long long)(avail == (size_t)-1 ? n : avail); d.frame0 = (int)frame0;
     d.win = (int)win; d.hop = (int)hop; d.pad_l = (int)((n_fft - win) / 2);
     d.n_frames = (int)T; d.win_f = tt.win_f.p; d.out = out; d.n_out = (int)n_out;
     d.mel_lo = tt.mel_lo.p; d.mel_cnt = tt.mel_cnt.p; d.mel_off = tt.mel_off.p; d.mel_w = tt.mel_w.p;
@@ -288,7 +289,11 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         const PcmSource &s = srcs[i];
         if (!s.data || s.n == 0 || s.ch == 0 || s.sr == 0) throw Error(SGX_ERR_BAD_ARG, "empty track");
         derive_params(s.sr, &pre[i].win, &pre[i].hop, &pre[i].n_fft);
-        check_stft_args(s.n, pre[i].win, pre[i].hop, pre[i].n_fft, &pre[i].T);
+        check_stft_args(s.n_total ? s.n_total : s.n, pre[i].win, pre[i].hop, pre[i].n_fft, &pre[i].T);
+        if (s.n_total) { // time slice of a longer track
+            if (s.origin + s.n > s.n_total || s.frame_count == 0 || s.frame_begin + s.frame_count > (size_t)pre[i].T)
+                throw Error(SGX_ERR_BAD_ARG, "time slice outside the track");
+        }
     }
     // ---- insert tracks (lib.rs:174-187) --------------------------------------------------------------
     // host-resident PCM is uploaded on a second stream, track by track, and every track's analysis starts as
@@ -314,7 +319,9 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         auto it = tracks_.find(ids[i]);
         if (it == tracks_.end()) it = tracks_.emplace(ids[i], Track()).first;
         Track &t = it->second;
-        t.path = s.path; t.sr = s.sr; t.ch = s.ch; t.fmt = s.fmt; t.n = s.n;
+        t.path = s.path; t.sr = s.sr; t.ch = s.ch; t.fmt = s.fmt;
+        t.n = s.n_total ? s.n_total : s.n; t.avail = s.n; t.origin = s.n_total ? s.origin : 0;
+        t.is_slice = s.n_total != 0;
         t.win = pre[i].win; t.hop = pre[i].hop; t.n_fft = pre[i].n_fft;
         t.tables = tables_for(s.sr, t.win, t.n_fft);
         const size_t esz = s.fmt == PCM_I16 ? 2 : 4;
@@ -327,7 +334,9 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
             copy_event_of[ids[i]] = i;
             t.d_pcm = t.owned_pcm.p;
         }
-        t.n_frames = (size_t)pre[i].T;
+        t.t_total = (size_t)pre[i].T;
+        t.frame0 = t.is_slice ? s.frame_begin : 0;
+        t.n_frames = t.is_slice ? s.frame_count : (size_t)pre[i].T;
         t.n_out = t.tables->n_mel ? t.tables->n_mel : t.n_fft / 2 + 1;
         t.spec.ensure(t.n_frames * t.n_out);
         if (t.slot < 0) t.slot = alloc_slot();
@@ -359,7 +368,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         for (size_t id : uniq) {
             Track &t = tracks_.at(id);
             StftTrack d = make_desc(t.d_pcm, t.fmt, t.n, t.ch, t.win, t.hop, t.n_fft, t.n_frames, *t.tables,
-                                    t.spec.p, t.n_out, slots_.p + 2 * t.slot);
+                                    t.spec.p, t.n_out, slots_.p + 2 * t.slot, t.origin, t.avail, t.frame0);
             d.tile_begin = pipelined ? 0 : g.n_tiles; // pipelined: one launch per track
             g.n_tiles += (int)((t.n_frames + g.tiling.frames_per_tile - 1) / g.tiling.frames_per_tile);
             descs.push_back(d);
@@ -465,21 +474,25 @@ AxisTableDev *MultiTrack::axis_table(int n_in, int n_out, bool tap_major)
 }
 
 void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32_t nheight, int channels,
-                        uint8_t *const *d_out, const size_t *cap, size_t *written)
+                        uint8_t *const *d_out, const size_t *cap, size_t *written, const uint32_t *ox_begin,
+                        const uint32_t *ox_count)
 {
     SGX_CUDA(cudaSetDevice(device_));
     if (channels != 3 && channels != 4) throw Error(SGX_ERR_BAD_ARG, "channels must be 3 or 4");
     if (nheight > 65535u) throw Error(SGX_ERR_BAD_ARG, "nheight too large");
     const bool mel = set_.freq_scale == SGX_FREQ_MEL;
     const uint32_t msr = effective_max_sr();
-    struct Item { size_t idx; int T, height, nwidth; };
+    struct Item { size_t idx; int T, height, nwidth, cols; };
     std::vector<Item> items;
     std::vector<RenderTrack> descs;
     bool short_buf = false;
     for (size_t i = 0; i < ids.size(); ++i) {
         const Track &t = track(ids[i]);
         const uint32_t nwidth = calc_nwidth(px_per_sec, t.n, t.sr); // lib.rs:296
-        const size_t need = (size_t)nwidth * nheight * channels;
+        // column window of this request (whole image unless a driver renders a strip of a time slice)
+        const uint32_t ob = ox_begin ? ox_begin[i] : 0, oc = ox_count ? ox_count[i] : nwidth;
+        if (ob > nwidth || oc > nwidth - ob) throw Error(SGX_ERR_BAD_ARG, "column window outside the image");
+        const size_t need = (size_t)oc * nheight * channels;
         if (written) written[i] = need;
         if (need == 0) continue;
         if (!d_out || !d_out[i]) continue; // size query
@@ -489,13 +502,21 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
         if (height < t.n_out)
             throw Error(SGX_ERR_STATE, "up_ratio < 1: u32 underflow at display.rs:47 (global max_sr not set?)");
         RenderTrack r{};
-        r.src = t.spec.p; r.width = (int)t.n_frames; r.n_out = (int)t.n_out; r.height = (int)height;
+        r.src = t.spec.p; r.width = (int)t.t_total; r.n_out = (int)t.n_out; r.height = (int)height;
+        r.frame0 = (int)t.frame0; r.src_frames = (int)t.n_frames; r.ox_begin = (int)ob; r.ox_count = (int)oc;
         r.nwidth = (int)nwidth; r.nheight = (int)nheight; r.out = d_out[i];
+        if (t.is_slice) { // the strip may only need frames this handle holds
+            uint32_t l0, r0, l1, r1;
+            lanczos3_span((uint32_t)t.t_total, nwidth, ob, &l0, &r0);
+            lanczos3_span((uint32_t)t.t_total, nwidth, ob + oc - 1, &l1, &r1);
+            if (l0 < t.frame0 || r1 > t.frame0 + t.n_frames)
+                throw Error(SGX_ERR_BAD_ARG, "time slice does not hold the frames this column window needs (see sgx_slice_plan)");
+        }
         AxisTableDev *v = axis_table((int)height, (int)nheight, false);
-        AxisTableDev *h = axis_table((int)t.n_frames, (int)nwidth, true);
+        AxisTableDev *h = axis_table((int)t.t_total, (int)nwidth, true);
         r.v_left = v->left.p; r.v_cnt = v->cnt.p; r.v_sum = v->sum.p; r.v_w = v->w.p; r.v_taps = v->taps;
         r.h_left = h->left.p; r.h_cnt = h->cnt.p; r.h_sum = h->sum.p; r.h_w = h->w.p; r.h_taps = h->taps;
-        items.push_back(Item{descs.size(), r.width, r.height, r.nwidth});
+        items.push_back(Item{descs.size(), r.width, r.height, r.nwidth, r.ox_count});
         descs.push_back(r);
     }
     if (!descs.empty()) {
@@ -514,12 +535,14 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
             while (b < items.size() && items[b].T == items[a].T && items[b].height == items[a].height &&
                    items[b].nwidth == items[a].nwidth) ++b;
             const RenderTiling tl = plan_render_tiles(items[a].T, items[a].height, items[a].nwidth, (int)nheight);
+            int max_cols = 0;
+            for (size_t c = a; c < b; ++c) max_cols = std::max(max_cols, items[c].cols);
             for (size_t c = a; c < b; c += 65535) { // gridDim.z limit
                 RenderLaunch L{};
                 L.tracks = d_render_.p + c; L.n_tracks = (int)std::min<size_t>(65535, b - c);
                 L.from_db = 1; L.range = d_state_.p; L.channels = channels;
                 L.px = tl.px; L.py = tl.py; L.fc = tl.fc; L.rv_max = tl.rv_max;
-                SGX_CUDA(launch_render(L, items[a].nwidth, (int)nheight, tl.smem_bytes, tl.fast, stream_));
+                SGX_CUDA(launch_render(L, max_cols, (int)nheight, tl.smem_bytes, tl.fast, stream_));
             }
             a = b;
         }
@@ -558,6 +581,7 @@ std::vector<uint8_t> MultiTrack::wav_image(size_t id, float px_per_sec, uint32_t
 {
     SGX_CUDA(cudaSetDevice(device_));
     const Track &t = track(id);
+    if (t.is_slice) throw Error(SGX_ERR_STATE, "get_wav_image is not available for a time slice of a track");
     const uint32_t nwidth = calc_nwidth(px_per_sec, t.n, t.sr); // lib.rs:308
     const size_t need = (size_t)nwidth * nheight * 4;
     std::vector<uint8_t> host(need);
@@ -676,6 +700,7 @@ void stage_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint3
     SGX_CUDA(launch_build_axis_table((int)width, (int)nwidth, h.taps, true, h.left.p, h.cnt.p, h.sum.p, h.w.p, s));
     RenderTrack r{};
     r.src = dg.p; r.width = (int)width; r.n_out = (int)height; r.height = (int)height;
+    r.frame0 = 0; r.src_frames = (int)width; r.ox_begin = 0; r.ox_count = (int)nwidth;
     r.nwidth = (int)nwidth; r.nheight = (int)nheight; r.out = dout.p;
     r.v_left = v.left.p; r.v_cnt = v.cnt.p; r.v_sum = v.sum.p; r.v_w = v.w.p; r.v_taps = v.taps;
     r.h_left = h.left.p; r.h_cnt = h.cnt.p; r.h_sum = h.sum.p; r.h_w = h.w.p; r.h_taps = h.taps;

@@ -80,7 +80,10 @@ struct Track {
     std::string path;
     uint32_t sr = 0, ch = 1;
     int fmt = PCM_F32;
-    size_t n = 0;             // samples per channel
+    size_t n = 0;             // samples per channel of the whole track
+    size_t avail = 0, origin = 0; // samples present at d_pcm and the global index of the first one
+    bool is_slice = false;    // the handle holds a time slice of the track (n3: one track over several GPUs)
+    size_t t_total = 0, frame0 = 0; // frames of the whole track; global index of spec row 0
     size_t win = 0, hop = 0, n_fft = 0;
     const void *d_pcm = nullptr;
     DevBuf<unsigned char> owned_pcm;
@@ -92,6 +95,9 @@ struct Track {
 
 struct PcmSource {
     const void *data; int fmt; size_t n; uint32_t sr; uint32_t ch; bool on_device; std::string path;
+    // time slice of a longer track (n_total != 0): `data` holds samples [origin, origin + n) of a track of
+    // n_total samples and frames [frame_begin, frame_begin + frame_count) are to be analysed
+    size_t n_total = 0, origin = 0, frame_begin = 0, frame_count = 0;
 };
 
 class DeviceCtx {
@@ -116,7 +122,8 @@ public:
     bool remove_track(size_t id, bool want_changed);    // lib.rs:265-292
     // lib.rs:294-298 (channels 3) / RGBA; device output, asynchronous
     void render(const std::vector<size_t> &ids, float px_per_sec, uint32_t nheight, int channels,
-                uint8_t *const *d_out, const size_t *cap, size_t *written);
+                uint8_t *const *d_out, const size_t *cap, size_t *written, const uint32_t *ox_begin = nullptr,
+                const uint32_t *ox_count = nullptr);
     void render_host(size_t id, float px_per_sec, uint32_t nheight, int channels, uint8_t *out, size_t need);
     void set_profiling(bool on);
     void stage_times(float *analysis_ms, float *render_ms);

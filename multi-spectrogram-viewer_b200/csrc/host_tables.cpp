@@ -167,6 +167,19 @@ uint32_t grey_height(size_t n_out, float up_ratio)
     return (uint32_t)std::round((float)n_out * up_ratio);
 }
 
+void lanczos3_span(uint32_t n_in, uint32_t n_out, uint32_t o, uint32_t *left, uint32_t *right)
+{
+    const float ratio = (float)n_in / (float)n_out;
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    const float support = 3.0f * sratio;
+    const float inputx = ((float)o + 0.5f) * ratio;
+    long long l = (long long)std::floor(inputx - support);
+    l = l < 0 ? 0 : (l > (long long)n_in - 1 ? (long long)n_in - 1 : l);
+    long long r = (long long)std::ceil(inputx + support);
+    r = r < l + 1 ? l + 1 : (r > (long long)n_in ? (long long)n_in : r);
+    *left = (uint32_t)l; *right = (uint32_t)r;
+}
+
 MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group,
                         size_t stage_capacity_floats)
 {

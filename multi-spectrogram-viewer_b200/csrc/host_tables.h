@@ -30,6 +30,9 @@ uint32_t calc_nwidth(float px_per_sec, size_t n, uint32_t sr);
 float calc_up_ratio(uint32_t max_sr, uint32_t sr, bool mel);
 // display.rs:45
 uint32_t grey_height(size_t n_out, float up_ratio);
+// tap window [left, right) of output index o when resampling n_in -> n_out with image 0.23's Lanczos3
+// (same f32 operations as the device table builder)
+void lanczos3_span(uint32_t n_in, uint32_t n_out, uint32_t o, uint32_t *left, uint32_t *right);
 
 // Banded (CSR-by-filter) form of a [n_freq][n_mel] filterbank for the device projection.
 struct MelBands {

@@ -160,9 +160,10 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaun
     __shared__ float cm[30];
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
     const int nwidth = tr->nwidth, nheight = tr->nheight;
-    const int ox0 = blockIdx.x * L.px, oy0 = blockIdx.y * L.py;
-    if (ox0 >= nwidth || oy0 >= nheight) return;
-    const int pxc = min(L.px, nwidth - ox0), pyc = min(L.py, nheight - oy0);
+    const int ox_end = tr->ox_begin + tr->ox_count; // this launch renders columns [ox_begin, ox_end)
+    const int ox0 = tr->ox_begin + blockIdx.x * L.px, oy0 = blockIdx.y * L.py;
+    if (ox0 >= ox_end || oy0 >= nheight) return;
+    const int pxc = min(L.px, ox_end - ox0), pyc = min(L.py, nheight - oy0);
     const int tid = threadIdx.x;
     if (tid < 30) cm[tid] = (float)kColormap[tid / 3][tid % 3];
 
@@ -201,8 +202,9 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaun
             const int y = yl + yy;
             float g;
             if (L.from_db) {
-                if (y >= pad_rows) {
-                    const float db = __ldg(src + (size_t)(c0 + fx) * n_out + (height - 1 - y));
+                const int lf = c0 + fx - tr->frame0; // row of the (possibly time-sliced) dB array
+                if (y >= pad_rows && lf >= 0 && lf < tr->src_frames) {
+                    const float db = __ldg(src + (size_t)lf * n_out + (height - 1 - y));
                     g = fminf(fmaxf(__fdiv_rn(__fsub_rn(db, min_db), inv_span), 0.0f), 1.0f);
                 } else g = 0.0f;
             } else {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaun
             const int ox = ox0 + oxl, oy = oy0 + oyl;
             const float g = clamp_pos(__fdiv_rn(acc[q], tr->h_sum[ox]));
             const uchar4 c = grey_to_color(g, cm);
-            const size_t pix = (size_t)oy * nwidth + ox;
+            const size_t pix = (size_t)oy * tr->ox_count + (ox - tr->ox_begin);
             if (L.channels == 4) reinterpret_cast<uchar4 *>(outp)[pix] = c;
             else { outp[pix * 3] = c.x; outp[pix * 3 + 1] = c.y; outp[pix * 3 + 2] = c.z; }
         }
@@ -308,9 +310,11 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? 4 : 1) 
     float *Tm = rsm + RCAP * GP;         // [frame][out row]
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
     const int nwidth = tr->nwidth, nheight = tr->nheight;
-    const int ox0 = blockIdx.x * kFpTile, oy0 = blockIdx.y * kFpTile;
-    if (ox0 >= nwidth || oy0 >= nheight) return;
-    const int pxc = min(kFpTile, nwidth - ox0), pyc = min(kFpTile, nheight - oy0);
+    const int ox_begin = tr->ox_begin, ox_count = tr->ox_count, frame0 = tr->frame0, src_frames = tr->src_frames;
+    const int ox_end = ox_begin + ox_count; // this launch renders columns [ox_begin, ox_end)
+    const int ox0 = ox_begin + blockIdx.x * kFpTile, oy0 = blockIdx.y * kFpTile;
+    if (ox0 >= ox_end || oy0 >= nheight) return;
+    const int pxc = min(kFpTile, ox_end - ox0), pyc = min(kFpTile, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3], (float)kColormap[tid / 3 + 1][tid % 3]);
 
@@ -356,9 +360,10 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? 4 : 1) 
         for (int fq = warp; fq < nfq; fq += kRenderThreads / 32) {
             const int fx = fq * 4 + fsub;
             const int f = fl + fx;
-            const bool fok = f < width;
-            // FROM_DB: element (frame f, grey row y) is dB[f][height-1-y]; else grey[y][f]
-            const float *__restrict__ p0 = FROM_DB ? src + (size_t)(fok ? f : 0) * n_out + (height - 1 - yl - rsub)
+            const int lf = FROM_DB ? f - frame0 : f; // row of the (possibly time-sliced) dB array
+            const bool fok = f < width && lf >= 0 && (!FROM_DB || lf < src_frames);
+            // FROM_DB: element (frame f, grey row y) is dB[lf][height-1-y]; else grey[y][f]
+            const float *__restrict__ p0 = FROM_DB ? src + (size_t)(fok ? lf : 0) * n_out + (height - 1 - yl - rsub)
                                                    : src + (size_t)(yl + rsub) * width + (fok ? f : 0);
             float *g0 = G + rsub * GP + fx;
             for (int j0 = 0; j0 < nrow; j0 += 32) {
@@ -424,9 +429,10 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? 4 : 1) 
                     t[0] = fmaf(v.x, wh[i], t[0]); t[1] = fmaf(v.y, wh[i], t[1]);
                     t[2] = fmaf(v.z, wh[i], t[2]); t[3] = fmaf(v.w, wh[i], t[3]);
                 }
-                size_t pix = (size_t)(oy0 + rq * 4) * nwidth + ox;
+                const int opitch = ox_count;
+                size_t pix = (size_t)(oy0 + rq * 4) * opitch + (ox - ox_begin);
 #pragma unroll
-                for (int j = 0; j < 4; ++j, pix += nwidth) {
+                for (int j = 0; j < 4; ++j, pix += opitch) {
                     if (rq * 4 + j < pyc) {
                         const unsigned c = grey_to_rgba_fast(clamp_pos(t[j]), cmab);
                         if (CH == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;

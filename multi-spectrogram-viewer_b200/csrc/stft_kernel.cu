@@ -108,12 +108,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // ---- sample access: channel sum + reflect (lib.rs:42, utils.rs:79-85) ---------------------------
 struct PcmView {
     const void *pcm; long long n; int ch; int fmt;
+    long long origin, avail; // time slices: pcm[0] is global sample `origin`, `avail` samples are present
 };
 __device__ __forceinline__ float load_sample(const PcmView &pv, long long i)
 {
     if (i < 0) i = -i;                         // left reflect, edge sample not repeated
     if (i >= pv.n) i = 2 * (pv.n - 1) - i;     // right reflect
     i = i < 0 ? 0 : (i >= pv.n ? pv.n - 1 : i); // only reachable under zero window weight
+    i -= pv.origin;                            // global -> local index of a time slice
+    i = i < 0 ? 0 : (i >= pv.avail ? pv.avail - 1 : i);
     float s = 0.0f;
     if (pv.fmt == PCM_F32) {
         const float *p = reinterpret_cast<const float *>(pv.pcm) + i * pv.ch;
@@ -354,7 +357,7 @@ stft_db_kernel(const StftLaunch L)
         if (L.tracks[mid].tile_begin <= tile_id) lo = mid; else hi = mid - 1;
     }
     const StftTrack *__restrict__ td = L.tracks + lo;
-    const PcmView pv{td->pcm, td->n, td->ch, td->fmt};
+    const PcmView pv{td->pcm, td->n, td->ch, td->fmt, td->origin, td->avail};
     const int win = td->win, hop = td->hop, pad_l = td->pad_l, T = td->n_frames;
     const float *__restrict__ win_f = td->win_f;
     float *__restrict__ out = td->out;
@@ -363,9 +366,9 @@ stft_db_kernel(const StftLaunch L)
 
     const int t0 = (tile_id - td->tile_begin) * L.frames_per_tile;
     const int nfr = min(L.frames_per_tile, T - t0);
-    const long long S0 = (long long)t0 * hop - win / 2 - pad_l; // first sample of frame t0 (FFT frame)
-    const int off0 = (int)(S0 & 3);
-    const long long A0 = S0 - off0; // 16-byte aligned start of the staged tile
+    const long long S0 = (long long)(td->frame0 + t0) * hop - win / 2 - pad_l; // first (global) sample of the tile's first FFT frame
+    const int off0 = (int)((S0 - pv.origin) & 3);
+    const long long A0 = S0 - off0; // global index whose LOCAL position is 16-byte aligned: start of the staged tile
     const bool vec_ok = ((hop | off0) & 1) == 0; // all frames of the tile start on an even float
 
     // ---- stage the PCM tile ------------------------------------------------------------------------
@@ -373,14 +376,14 @@ stft_db_kernel(const StftLaunch L)
         const int len = off0 + (nfr - 1) * hop + F;
         const int len4 = (len + 3) & ~3;
         const bool tma = pv.ch == 1 && pv.fmt == PCM_F32 &&
-                         ((reinterpret_cast<uintptr_t>(pv.pcm) & 15) == 0) && A0 >= 0 &&
-                         A0 + len4 <= pv.n;
+                         ((reinterpret_cast<uintptr_t>(pv.pcm) & 15) == 0) && A0 >= 0 && A0 + len4 <= pv.n &&
+                         A0 - pv.origin >= 0 && A0 - pv.origin + len4 <= pv.avail;
         if (tma) {
             if (tid == 0) mbar_init(mbar, 1);
             __syncthreads();
             if (tid == 0) {
                 mbar_expect_tx(mbar, (unsigned)len4 * 4u);
-                bulk_copy_g2s(tile, reinterpret_cast<const float *>(pv.pcm) + A0,
+                bulk_copy_g2s(tile, reinterpret_cast<const float *>(pv.pcm) + (A0 - pv.origin),
                               (unsigned)len4 * 4u, mbar);
             }
             mbar_wait(mbar, 0);
@@ -765,17 +768,19 @@ __global__ void __launch_bounds__(kWThreads, 1) stft_warp_kernel(const StftLaunc
         while (nxt + 1 < L.n_tracks && L.tracks[nxt + 1].tile_begin <= g) ++nxt;
         if (nxt != cur) { flush_range(L.tracks + cur); cur = nxt; }
         const StftTrack *__restrict__ td = L.tracks + cur;
-        const PcmView pv{td->pcm, td->n, td->ch, td->fmt};
+        const PcmView pv{td->pcm, td->n, td->ch, td->fmt, td->origin, td->avail};
         const int t = g - td->tile_begin;
-        const long long S0 = (long long)t * td->hop - td->win / 2 - td->pad_l;
+        const long long S0 = (long long)(td->frame0 + t) * td->hop - td->win / 2 - td->pad_l; // global
+        const long long Sl = S0 - pv.origin;                                                  // local to the slice
         float *__restrict__ out = td->out;
         const int n_out = td->n_out;
 
         float re[32][1], im[32][1];
         // ---- A: windowed samples, z[32 m1 + lane] = (g[2m], g[2m+1]) ------------------------------------------
-        const bool interior = pv.ch == 1 && pv.fmt == PCM_F32 && S0 >= 0 && S0 + 2 * kWH <= pv.n;
-        if (interior && ((S0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(pv.pcm) & 7) == 0)) {
-            const float2 *__restrict__ p = reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(pv.pcm) + S0) + lane;
+        const bool interior = pv.ch == 1 && pv.fmt == PCM_F32 && S0 >= 0 && S0 + 2 * kWH <= pv.n && Sl >= 0 &&
+                              Sl + 2 * kWH <= pv.avail;
+        if (interior && ((Sl & 1) == 0) && ((reinterpret_cast<uintptr_t>(pv.pcm) & 7) == 0)) {
+            const float2 *__restrict__ p = reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(pv.pcm) + Sl) + lane;
 #pragma unroll
             for (int m1 = 0; m1 < 32; ++m1) {
                 const float2 x = __ldg(p + 32 * m1);
@@ -783,7 +788,7 @@ __global__ void __launch_bounds__(kWThreads, 1) stft_warp_kernel(const StftLaunc
                 re[m1][0] = x.x * w.x; im[m1][0] = x.y * w.y;
             }
         } else if (interior) {
-            const float *__restrict__ p = reinterpret_cast<const float *>(pv.pcm) + S0 + 2 * lane;
+            const float *__restrict__ p = reinterpret_cast<const float *>(pv.pcm) + Sl + 2 * lane;
 #pragma unroll
             for (int m1 = 0; m1 < 32; ++m1) {
                 const float2 w = win2[32 * m1 + lane];
@@ -914,10 +919,10 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, i
         if (L.tracks[mid].tile_begin <= tile_id) lo = mid; else hi = mid - 1;
     }
     const StftTrack *__restrict__ td = L.tracks + lo;
-    const PcmView pv{td->pcm, td->n, td->ch, td->fmt};
+    const PcmView pv{td->pcm, td->n, td->ch, td->fmt, td->origin, td->avail};
     const int t = tile_id - td->tile_begin; // one frame per CTA
     const int F = 2 * h, n_out = td->n_out, mode = L.mode;
-    const long long S0 = (long long)t * td->hop - td->win / 2 - td->pad_l;
+    const long long S0 = (long long)(td->frame0 + t) * td->hop - td->win / 2 - td->pad_l;
     float *__restrict__ out = td->out;
 
     for (int m = tid; m < h; m += blockDim.x) {

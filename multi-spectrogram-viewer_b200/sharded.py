@@ -88,6 +88,28 @@ class ShardedMultiTrack:
             all_reduce_range(self._range, self.group)  # NCCL, 8 bytes, ordered on the engine's stream
         self.mt.commit_range_device()
 
+    def add_track_time_sharded(self, id: int, pcm_host: np.ndarray, sr: int, px_per_sec: float, rank: int, world: int):
+        """n3: ONE long track over `world` GPUs.  This rank takes a strip of output columns, uploads only the samples
+        that strip's frames read, analyses them and joins the global range exchange.  pcm_host is the whole track
+        ([n] or interleaved [n, ch] float32) -- only this rank's chunk is copied.  Returns (ox_begin, ox_count)."""
+        from . import calc_nwidth_like, slice_plan
+
+        torch = self.torch
+        n_total = pcm_host.shape[0]
+        ch = 1 if pcm_host.ndim == 1 else pcm_host.shape[1]
+        nwidth = calc_nwidth_like(px_per_sec, n_total, sr)
+        ob = nwidth * rank // world
+        oc = nwidth * (rank + 1) // world - ob
+        fb, fc, sb, sc = slice_plan(n_total, sr, px_per_sec, ob, oc, self.mt.settings)
+        chunk = torch.from_numpy(np.ascontiguousarray(pcm_host[sb:sb + sc], dtype=np.float32)).to(f"cuda:{self.device}")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self.mt.add_track_slice_device(id, chunk.data_ptr(), sb, sc, n_total, sr, ch, fb, fc, keepalive=chunk)
+        self.mt.set_global_max_sr(sr)
+        with torch.cuda.stream(self.stream):
+            all_reduce_range(self._range, self.group)
+        self.mt.commit_range_device()
+        return ob, oc
+
     def remove_track(self, id: int, owned: bool) -> None:
         if owned:
             self.mt.remove_track(id, sync=False)

@@ -46,6 +46,22 @@ def main():
         ok = ok and same
         print(f"rank {rank}: track {t} sr={srs[t]} pixels identical to single-process: {same}", flush=True)
     print(f"rank {rank}: range sharded {got_range} single {want_range}", flush=True)
+    # ---- n3: ONE long track time-sharded over all ranks (strips of columns) -----------------------------------
+    sr2 = 48000
+    long_track = synth.base_clip(90 * sr2 + 123, sr2, seed=4242)
+    st2 = msv.ShardedMultiTrack(device=local)
+    ob, oc = st2.add_track_time_sharded(0, long_track, sr2, 100.0, rank, world)
+    strip = torch.empty(300 * oc * 4, dtype=torch.uint8, device="cuda")
+    st2.mt.render_slice_device(0, 100.0, 300, 4, ob, oc, strip.data_ptr(), strip.numel())
+    st2.synchronize()
+    one = msv.MultiTrack(device=local)
+    one.add_tracks_pcm([0], [long_track], [sr2])
+    full = one.get_spec_image_rgba(0, 100.0, 300).reshape(300, -1, 4)
+    same = np.array_equal(strip.cpu().numpy().reshape(300, oc, 4), full[:, ob:ob + oc]) and \
+        (st2.get_max_db(), st2.get_min_db()) == (one.get_max_db(), one.get_min_db())
+    print(f"rank {rank}: time-sharded strip [{ob}, {ob + oc}) identical to the single-GPU image: {same}", flush=True)
+    ok = ok and same
+    st2.close(); one.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     sm.close(); ref.close()

@@ -135,3 +135,52 @@ print("K1W OK")
     env = dict(os.environ, SGX_K1W="1")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "K1W OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("sr,seconds,px,settings_kw", [
+    (48000, 40, 100.0, {}),                                                    # defaults: n_fft 2048, ratio ~1 (8-tap path)
+    (44100, 21, 100.0, {}),                                                    # odd hop 441
+    (48000, 30, 100.0, dict(win_length=4096, hop_length=256, n_fft=4096, n_mel=128)),  # C3 shape, 16-tap horizontal path
+    (16000, 25, 7.5, {}),                                                      # zoomed out: general render path
+    (22050, 9, 400.0, dict(freq_scale=0)),                                     # zoomed in, linear scale
+])
+def test_time_sliced_track_equals_whole_track(msv, sr, seconds, px, settings_kw):
+    """n3: one track cut into time slices -- each holding only the samples its strip of columns needs --
+    must give, strip by strip, exactly the pixels of the whole-track image, and the same dB range."""
+    torch = _torch()
+    st = msv.Settings.default(**settings_kw)
+    n = seconds * sr + 311
+    x = synth.base_clip(n, sr, seed=sr + seconds)
+    whole = msv.MultiTrack(st)
+    whole.add_tracks_pcm([0], [x], [sr])
+    nw = whole.image_width(0, px)
+    ref = whole.get_spec_image_rgba(0, px, 200).reshape(200, nw, 4)
+    ref_range = (whole.get_max_db(), whole.get_min_db())
+    whole.close()
+
+    parts = 5
+    mt = msv.MultiTrack(st)           # one handle stands in for `parts` ranks: the slots of all slices are reduced together
+    keep, strips = [], []
+    for r in range(parts):
+        ob = nw * r // parts
+        oc = nw * (r + 1) // parts - ob
+        fb, fc, sb, sc = msv.slice_plan(n, sr, px, ob, oc, st)
+        assert sc < n or parts == 1                                   # a slice really is a part of the track
+        chunk = torch.from_numpy(x[sb:sb + sc].copy()).cuda()
+        keep.append(chunk)
+        mt.add_track_slice_device(r, chunk.data_ptr(), sb, sc, n, sr, 1, fb, fc)
+        strips.append((ob, oc))
+    mt.commit_range_device()
+    mt.set_global_max_sr(sr)
+    outs = []
+    for r, (ob, oc) in enumerate(strips):
+        o = torch.empty(200 * oc * 4, dtype=torch.uint8, device="cuda")
+        assert mt.render_slice_device(r, px, 200, 4, ob, oc, o.data_ptr(), o.numel()) == o.numel()
+        outs.append(o)
+    mt.synchronize()
+    assert (mt.get_max_db(), mt.get_min_db()) == ref_range
+    got = np.concatenate([o.cpu().numpy().reshape(200, oc, 4) for o, (ob, oc) in zip(outs, strips)], axis=1)
+    assert np.array_equal(got, ref)
+    with pytest.raises(msv.SgxError):                                  # a strip this slice does not cover
+        mt.render_slice_device(0, px, 200, 4, strips[2][0], strips[2][1], outs[2].data_ptr(), outs[2].numel())
+    mt.close()
