@@ -43,6 +43,12 @@ def workload(name):
         return dict(sr=48000, seconds=3600, channels=2, tracks=1, seed=3003,
                     settings=dict(win_length=4096, hop_length=256, n_fft=4096, n_mel=128),
                     desc="C3: 1 h x 48 kHz stereo, n_fft=4096 hop=256 Hann, mel-128, dB + RGBA 100 px/s x 500")
+    if name == "c3s":  # n3: ONE track time-sharded over the GPUs (strong scaling)
+        w = workload("c3")
+        w["desc"] = "C3 time-sharded: ONE 1 h x 48 kHz stereo track, every GPU analyses and renders a strip of columns " \
+                    "(n_fft=4096 hop=256, mel-128, RGBA 100 px/s x 500); strong scaling"
+        w["sliced"] = True
+        return w
     if name == "c2":
         return dict(sr=48000, srs=[8000, 16000, 22050, 24000, 44100, 48000], seconds=44.032, channels=1, tracks=6, seed=2002,
                     settings=dict(n_mel=128),
@@ -183,6 +189,8 @@ def run_gpu(args, wl, rank, world, local_rank):
     # ---- synthetic batch, derived on the device from one uploaded base clip ----
     gids = [rank + i * world for i in range(ntr)]  # track t -> GPU t mod G
     tracks = []
+    if wl.get("sliced"):
+        return run_gpu_sliced(args, wl, rank, world, local_rank, st, n, sr, ch, dev)
     if "srs" in wl:  # mixed sample rates: one clip per rate (every GPU holds the same six tracks)
         srs = list(wl["srs"])
         ns = [int(round(wl["seconds"] * r)) for r in srs]
@@ -353,13 +361,93 @@ def run_gpu(args, wl, rank, world, local_rank):
             "gpu_launches": int(launches), "clocks": clk, "db_range": rng}
 
 
+def run_gpu_sliced(args, wl, rank, world, local_rank, st, n, sr, ch, dev):
+    """One track, time-sharded: rank r owns the columns [nw*r/G, nw*(r+1)/G) (sgx_slice_plan)."""
+    import torch
+    import torch.distributed as dist
+
+    import msv_b200 as msv
+    import synth
+
+    base = synth.base_clip(n, sr, wl["seed"])
+    nw = msv.calc_nwidth_like(PX_PER_SEC, n, sr)
+    ob = nw * rank // world
+    oc = nw * (rank + 1) // world - ob
+    fb, fc, sb, sc = msv.slice_plan(n, sr, PX_PER_SEC, ob, oc, st)
+    x = torch.from_numpy(base[sb:sb + sc]).to(dev)
+    if ch == 2:
+        full_r = np.roll(base, 1234) * np.float32(0.75)
+        x = torch.stack([x, torch.from_numpy(full_r[sb:sb + sc]).to(dev)], dim=1).contiguous()
+    del base
+    sm = msv.ShardedMultiTrack(st, device=local_rank)
+    sm.mt.set_profiling(True)
+    sm.mt.set_global_max_sr(sr)
+    out = torch.empty(oc * NHEIGHT * 4, dtype=torch.uint8, device=dev)
+
+    def step():
+        sm.stream.wait_stream(torch.cuda.current_stream(dev))
+        sm.mt.add_track_slice_device(0, x.data_ptr(), sb, sc, n, sr, ch, fb, fc)
+        with torch.cuda.stream(sm.stream):
+            msv.sharded.all_reduce_range(sm._range, sm.group)
+        sm.mt.commit_range_device()
+        sm.mt.render_slice_device(0, PX_PER_SEC, NHEIGHT, 4, ob, oc, out.data_ptr(), out.numel())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = msv.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(sm.stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(sm.stream)
+    barrier()
+    launches = msv.kernel_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    k1s, k3s = [], []
+    for _ in range(3):
+        for _ in range(3):
+            step()
+        a, r = sm.mt.stage_times()
+        k1s.append(a); k3s.append(r)
+    sm.synchronize()
+    rng = (sm.get_max_db(), sm.get_min_db())
+    sm.close()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    alg_total = float(4 * ch * n + nw * NHEIGHT * 4)        # whole job, all GPUs
+    alg_rank = float(4 * ch * sc + oc * NHEIGHT * 4)        # this rank's launch
+    k1, k3 = float(np.median(k1s)), float(np.median(k3s))
+    roofline = {"bound": "hbm", "kernel": "stft_db_kernel (K1) on this rank's slice", "achieved": alg_rank / (k1 * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": alg_rank / (k1 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_rank, "kernel_ms": k1}
+    step_roof = {"achieved": alg_total / (ms_step * 1e-3) / 1e9, "frac": alg_total / (ms_step * 1e-3) / 1e9 / (peak * world),
+                 "k1_ms": k1, "k3_ms": k3, "step_ms": ms_step, "note": "whole job over all GPUs against N x the measured peak"}
+    return {"value": (n / sr) / (ms_step * 1e-3), "ms_per_step": ms_step, "roofline": roofline, "roofline_step": step_roof, "e2e": None,
+            "gpu_launches": int(launches), "clocks": clk, "db_range": rng, "scaling": "strong"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c2", "c1"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c3s", "c2", "c1"])
     ap.add_argument("--tracks", type=int, default=0, help="override tracks per GPU (profiling runs only)")
     ap.add_argument("--seconds", type=float, default=0, help="override track length (profiling runs only)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -400,7 +488,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     res = run_gpu(args, wl, rank, world, local_rank)
     cb = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not wl.get("sliced"):
         cb = run_cpu(wl, 3, 1)
     if world > 1:
         dist.barrier()
@@ -408,7 +496,7 @@ def main():
     if rank != 0:
         return 0
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg, "roofline": res["roofline"], "roofline_step": res["roofline_step"],
             "cpu_baseline": cb, "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
             "db_range": res["db_range"]}

@@ -15,6 +15,22 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+cudaError_t ensure_dynamic_smem(const void *func, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> granted;
+    if (bytes <= 48 * 1024) return cudaSuccess; // the default limit needs no opt-in
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &g = granted[std::make_pair(func, dev)];
+    if (bytes <= g) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) g = bytes;
+    return e;
+}
+
 void cuda_check(cudaError_t e, const char *what, const char *file, int line)
 {
     if (e == cudaSuccess) return;

@@ -66,6 +66,10 @@ cudaError_t launch_wav_image(const void *pcm, int fmt, int ch, long long n, int 
                              float amp_min, float amp_max, unsigned char *out, int *err_flag,
                              cudaStream_t s);
 
+// Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (the attribute is per device and
+// per function; thread-safe, remembers what was already granted).
+cudaError_t ensure_dynamic_smem(const void *func, size_t bytes);
+
 void count_launch(int n = 1);
 uint64_t launch_count();
 

@@ -625,12 +625,8 @@ cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight
 #define SGX_FAST(TV, TH, DB, CHN)                                                                             \
         if (tv == TV && th == TH && (L.from_db != 0) == DB && L.channels == CHN) {                           \
             auto kern = render_fast_kernel<TV, TH, DB, CHN>;                                                  \
-            static bool configured = false;                                                                   \
-            if (!configured) {                                                                                \
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem(TV, TH)); \
-                if (e != cudaSuccess) return e;                                                               \
-                configured = true;                                                                            \
-            }                                                                                                 \
+            cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), fp_smem(TV, TH));              \
+            if (e != cudaSuccess) return e;                                                                   \
             kern<<<grid, kRenderThreads, fp_smem(TV, TH), s>>>(L);                                            \
             err = cudaSuccess;                                                                                \
         }
@@ -642,13 +638,8 @@ cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight
         count_launch();
         return cudaGetLastError();
     }
-    static size_t configured = 48 * 1024;
-    if (smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem_bytes);
-        if (e != cudaSuccess) return e;
-        configured = smem_bytes;
-    }
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(render_kernel), smem_bytes);
+    if (e != cudaSuccess) return e;
     dim3 grid((max_nwidth + L.px - 1) / L.px, (max_nheight + L.py - 1) / L.py, L.n_tracks);
     render_kernel<<<grid, kRenderThreads, smem_bytes, s>>>(L);
     count_launch();

@@ -1003,12 +1003,8 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
     using TR = K1Traits<LOG2H, PTS, V, G, MC>;
     auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC>;
-    static size_t configured = 0; // per instantiation
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+    if (e != cudaSuccess) return e;
     kern<<<L.n_tiles, TR::THREADS, smem, stream>>>(L);
     count_launch();
     return cudaGetLastError();
@@ -1144,19 +1140,12 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t
     if (L.n_tiles <= 0) return cudaSuccess;
     if (cfg.warp_per_frame) {
         const size_t smem = k1w_smem_bytes(L.mel_nnz, L.mel_rows);
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(stft_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
-        static int sms = 0;
-        if (sms == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            if (sms <= 0) sms = 148;
-        }
+        cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(stft_warp_kernel), smem);
+        if (e != cudaSuccess) return e;
+        int sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
         const int grid = std::min(sms, (L.n_tiles + kWWarps - 1) / kWWarps);
         stft_warp_kernel<<<grid, kWThreads, smem, stream>>>(L, L.mel_nnz, L.mel_rows);
         count_launch();
@@ -1165,13 +1154,8 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t
     const size_t smem = cfg.generic ? cfg.fft_smem
                                     : 16 + (size_t)L.tile_floats * sizeof(float) + cfg.fft_smem;
     if (cfg.generic) {
-        static size_t configured = 48 * 1024;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(stft_generic_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
+        cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(stft_generic_kernel), smem);
+        if (e != cudaSuccess) return e;
         stft_generic_kernel<<<L.n_tiles, 128, smem, stream>>>(L, cfg.h);
         count_launch();
         return cudaGetLastError();
