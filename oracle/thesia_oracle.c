@@ -839,6 +839,7 @@ ORC_API int orc_convert_grey_to_color(float x, uint8_t *rgb)
 ORC_API int orc_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint32_t nwidth,
                             uint32_t nheight, int channels, uint8_t *out, int parallel)
 {
+    if (!nwidth || !nheight) return 0; /* an empty image: RgbImage::from_fn(0, h, ..) has no pixels */
     float *res = (float *)malloc(sizeof(float) * (size_t)nwidth * nheight);
     if (orc_resize_lanczos3(grey, width, height, nwidth, nheight, res, parallel)) { free(res); return -1; }
     int bad = 0;

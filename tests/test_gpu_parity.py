@@ -326,3 +326,77 @@ def test_wav_image_parity(msv, orc):
     got = mt.get_wav_image(0, 100.0, 100, -1.0, 1.0).reshape(100, 300, 4)
     assert np.array_equal(got, orc.wav_to_image(x, 300, 100, -1.0, 1.0))
     mt.close()
+
+
+# ---- edge cases: ragged batches, maximum sizes, buffer re-use, extreme render geometry ----------------------
+def test_ragged_batch_and_id_reuse(msv, orc):
+    """Tracks of very different lengths in ONE add_tracks call (tile prefix logic), then the same ids re-added with
+    other lengths / rates (device buffers and range slots are re-used, lib.rs HashMap::insert semantics)."""
+    sr = 22050
+    lens = [884, 885, 1500, 22050, 3 * 22050 + 7, 16 * 221 + 884, 40000]        # from the shortest legal input (n == win) up
+    wavs = [synth.base_clip(n, sr, seed=n) for n in lens]
+    imgs, mx, mn = _oracle_batch(orc, msv, wavs, [sr] * len(wavs), nheight=64, px=300.0)
+    mt = msv.MultiTrack()
+    mt.add_tracks_pcm(list(range(len(wavs))), wavs, [sr] * len(wavs))
+    assert_range_close((mt.get_max_db(), mt.get_min_db()), (mx, mn), what="ragged")
+    for i, im in enumerate(imgs):
+        got = mt.get_spec_image(i, 300.0, 64).reshape(64, -1, 3)
+        assert_pixels_close(got, im, f"ragged track {i} (n={lens[i]})")
+    # re-use ids with different content: longer, shorter, other sample rate
+    srs2 = [48000, 22050, 8000]
+    wavs2 = [synth.base_clip(n, r, seed=n + r) for n, r in zip([100000, 900, 30000], srs2)]
+    mt.add_tracks_pcm([4, 0, 2], wavs2, srs2)
+    all_w = [wavs2[1], wavs[1], wavs2[2], wavs[3], wavs2[0], wavs[5], wavs[6]]
+    all_sr = [22050, sr, 8000, sr, 48000, sr, sr]
+    imgs, mx, mn = _oracle_batch(orc, msv, all_w, all_sr, nheight=64, px=300.0)
+    assert_range_close((mt.get_max_db(), mt.get_min_db()), (mx, mn), what="after id re-use")
+    for i, im in enumerate(imgs):
+        assert_pixels_close(mt.get_spec_image(i, 300.0, 64).reshape(64, -1, 3), im, f"re-used track {i}")
+    mt.close()
+
+
+def test_maximum_fft_size_default_mel(msv, orc):
+    """n_fft = 16384 (the largest supported), 96 kHz, default mel bank (mel.rs:87-99 search), int16 stereo ingest."""
+    sr = 96000
+    st = msv.Settings.default(win_length=16384, hop_length=4096, n_fft=16384)
+    l = synth.base_clip_i16(3 * sr, sr, 12)
+    pcm = np.stack([l, np.roll(l, 77)], axis=1)
+    mt = msv.MultiTrack(st)
+    mt.add_tracks_pcm([0], [pcm], [sr])
+    mono = pcm[:, 0].astype(np.float32) / np.float32(32768) + pcm[:, 1].astype(np.float32) / np.float32(32768)
+    fb = msv.calc_mel_fb_default(sr, 16384)
+    ref = orc.calc_spec(mono, 16384, 4096, 16384, None, fb)
+    assert mt.spec_shape(0) == ref.shape
+    assert_db_close(mt.get_spec_db(0), ref, "n_fft 16384 default mel")
+    mt.close()
+
+
+def test_many_tracks_grow_range_slots(msv):
+    """More tracks than the initial 1024 range slots: the slot array grows without losing extrema."""
+    sr = 8000
+    base = synth.base_clip(400, sr, 3)
+    n_tr = 1100
+    wavs = [base * np.float32(0.5 + 0.5 * (i % 7) / 7.0) for i in range(n_tr)]
+    mt = msv.MultiTrack()
+    mt.add_tracks_pcm(list(range(n_tr)), wavs, [sr] * n_tr)
+    loud = msv.MultiTrack()
+    loud.add_tracks_pcm([0], [base * np.float32(0.5 + 0.5 * 6 / 7.0)], [sr])
+    assert mt.get_max_db() == loud.get_max_db()
+    assert np.array_equal(mt.get_spec_db(6), loud.get_spec_db(0))
+    assert mt.remove_track(6) in (True, False) and mt.get_sr(1099) == sr
+    mt.close(); loud.close()
+
+
+@pytest.mark.parametrize("px,nh", [(0.5, 1), (3.0, 7), (1000.0, 33), (100.0, 2000), (0.01, 10)])
+def test_extreme_render_geometry(msv, orc, px, nh):
+    """Strong minification (chunked general path), strong magnification, 1-pixel and empty images."""
+    sr = 16000
+    x = synth.base_clip(12 * sr, sr, 21)
+    imgs, mx, mn = _oracle_batch(orc, msv, [x], [sr], nheight=nh, px=px, channels=4)
+    mt = msv.MultiTrack()
+    mt.add_tracks_pcm([0], [x], [sr])
+    got = mt.get_spec_image_rgba(0, px, nh)
+    assert got.size == imgs[0].size
+    if got.size:
+        assert_pixels_close(got.reshape(imgs[0].shape), imgs[0], f"px={px} nh={nh}", max_mismatch_frac=0.02)
+    mt.close()
