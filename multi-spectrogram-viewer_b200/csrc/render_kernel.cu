@@ -272,6 +272,14 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const RenderLaun
 // Pitches of 84 and 68 floats (odd multiples of 4) keep the 8 lanes of every 128-bit phase on
 // distinct 16-byte bank groups while neighbouring lanes address neighbouring (or equal) rows.
 // ---------------------------------------------------------------------------------------------------
+#ifndef SGX_K3_ABATCH
+#define SGX_K3_ABATCH 8
+#endif
+#ifndef SGX_K3_CTAS
+#define SGX_K3_CTAS 4
+#endif
+constexpr int kABatch = SGX_K3_ABATCH; // 8-row load batches in flight per thread while the grey tile is filled
+constexpr int kFpCtas = SGX_K3_CTAS;   // resident CTAs the 8-tap kernel is compiled for
 constexpr int kFpTile = 64;     // output pixels per tile edge
 constexpr int kFpTP = 68;       // pitch of Tm [frame][out row]  (odd multiple of 4)
 // source frames / rows a tile can need with T taps per output index (n_in/n_out < (T-1)/6):
@@ -301,7 +309,7 @@ __device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const float2 *cma
 }
 
 template <int TV, int TH, bool FROM_DB, int CH>
-__global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? 4 : 1) render_fast_kernel(const RenderLaunch L)
+__global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas : 1) render_fast_kernel(const RenderLaunch L)
 {
     constexpr int RCAP = fp_cap(TV), FCAP = fp_cap(TH), GP = FCAP; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
@@ -366,18 +374,18 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? 4 : 1) 
             const float *__restrict__ p0 = FROM_DB ? src + (size_t)(fok ? lf : 0) * n_out + (height - 1 - yl - rsub)
                                                    : src + (size_t)(yl + rsub) * width + (fok ? f : 0);
             float *g0 = G + rsub * GP + fx;
-            for (int j0 = 0; j0 < nrow; j0 += 32) {
-                // four 8-row batches per trip, all loads issued before the first use
-                float v[4];
+            for (int j0 = 0; j0 < nrow; j0 += 8 * kABatch) {
+                // kABatch 8-row batches per trip, all loads issued before the first use
+                float v[kABatch];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kABatch; ++j) {
                     const int yy = j0 + j * 8 + rsub;
                     const bool ok = fok && yy >= yy_lo && yy < yy_hi;
                     v[j] = FROM_DB ? -INFINITY : 0.0f; // -inf -> grey 0 after the saturate
                     if (ok) v[j] = FROM_DB ? __ldg(p0 - (j0 + j * 8)) : __ldg(p0 + (size_t)(j0 + j * 8) * width);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kABatch; ++j) {
                     const int yy = j0 + j * 8 + rsub;
                     const float g = FROM_DB ? __saturatef((v[j] - min_db) * inv_span) : v[j];
                     if (yy < RCAP) g0[(j0 + j * 8) * GP] = g;
