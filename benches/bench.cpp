@@ -1,0 +1,110 @@
+// benches/bench.cpp -- the reference's four criterion benches (benches/bench.rs:32-95), same names and bodies,
+// against the C ABI of include/sgx.h.  The reference loads samples/sample.wav (a file that does not exist in its
+// tree); here a WAV path may be given, else 44.03 s of synthetic 48 kHz audio is used.
+//
+//   "get mel spectrogram"        bench.rs:62-77   1 s of audio, W=1920 hop=480 n_fft=2048, default mel bank, dB
+//   "draw spectrogram"           bench.rs:79-95   grey -> RGB, 100 px/s x 500
+//   "add track"                  bench.rs:32-45   6 x the same track through MultiTrack::add_tracks
+//   "multitrack get spec image"  bench.rs:47-60   get_spec_image(0, 100., 500)
+//
+// build: g++ -O2 -std=c++17 -I include benches/bench.cpp -L multi-spectrogram-viewer_b200 -lsgx -Wl,-rpath,'$ORIGIN/../multi-spectrogram-viewer_b200' -o benches/bench
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "sgx.h"
+
+static void check(int code, const char *what)
+{
+    if (code != SGX_OK) { std::fprintf(stderr, "%s failed: [%d] %s\n", what, code, sgx_last_error()); std::exit(1); }
+}
+
+static void bench_function(const char *name, const std::function<void()> &body)
+{
+    using clk = std::chrono::steady_clock;
+    for (int i = 0; i < 3; ++i) body(); // warm-up
+    std::vector<double> us;
+    const auto t_end = clk::now() + std::chrono::milliseconds(1500);
+    while (clk::now() < t_end || us.size() < 10) {
+        const auto t0 = clk::now();
+        body();
+        us.push_back(std::chrono::duration<double, std::micro>(clk::now() - t0).count());
+        if (us.size() >= 2000) break;
+    }
+    std::sort(us.begin(), us.end());
+    std::printf("%-28s time: [%10.2f us %10.2f us %10.2f us]  (%zu samples)\n", name, us.front(), us[us.size() / 2], us.back(), us.size());
+}
+
+int main(int argc, char **argv)
+{
+    std::vector<float> wav;
+    uint32_t sr = 48000;
+    if (argc > 1) { // audio::open_audio_file + sum_axis(Axis(0)), bench.rs:63-64
+        size_t n = 0; uint32_t ch = 0;
+        check(sgx_open_wav(argv[1], nullptr, 0, &n, &ch, &sr), "open_wav");
+        std::vector<float> inter(n * ch);
+        check(sgx_open_wav(argv[1], inter.data(), inter.size(), &n, &ch, &sr), "open_wav");
+        wav.assign(n, 0.0f);
+        for (size_t i = 0; i < n; ++i) for (uint32_t c = 0; c < ch; ++c) wav[i] += inter[i * ch + c];
+    } else {
+        wav.resize(2113529);
+        unsigned s = 12345u;
+        for (size_t i = 0; i < wav.size(); ++i) {
+            s = s * 1664525u + 1013904223u;
+            const double t = (double)i / sr;
+            wav[i] = (float)(0.1 * std::sin(6.283185307179586 * 440.0 * t) + 0.05 * std::sin(6.283185307179586 * 3520.0 * t) +
+                             0.01 * ((double)(s >> 8) / 8388608.0 - 1.0));
+        }
+    }
+    const size_t one_sec = std::min<size_t>(sr, wav.size());
+    // windows::hann(1920, false) / 2048., mel::calc_mel_fb_default(sr, 2048)   bench.rs:66-67
+    std::vector<float> window(1920);
+    check(sgx_calc_window(1920, 2048, window.data()), "calc_window");
+    size_t n_mel = 0;
+    check(sgx_calc_mel_fb_default(sr, 2048, nullptr, 0, &n_mel), "calc_mel_fb_default");
+    std::vector<float> mel_fb(1025 * n_mel);
+    check(sgx_calc_mel_fb_default(sr, 2048, mel_fb.data(), mel_fb.size(), &n_mel), "calc_mel_fb_default");
+    size_t T = 0;
+    check(sgx_melspectrogram_db(wav.data(), one_sec, 1920, 480, 2048, window.data(), mel_fb.data(), n_mel, nullptr, 0, &T), "melspectrogram size");
+    std::vector<float> spec(T * n_mel);
+
+    bench_function("get mel spectrogram", [&] {
+        check(sgx_melspectrogram_db(wav.data(), one_sec, 1920, 480, 2048, window.data(), mel_fb.data(), n_mel, spec.data(), spec.size(), &T),
+              "melspectrogram_db");
+    });
+
+    // display::spec_to_grey(spec, up_ratio = 1, max, min)   bench.rs:86 (with the 4-argument signature of display.rs:44)
+    const float mx = *std::max_element(spec.begin(), spec.end()), mn = *std::min_element(spec.begin(), spec.end());
+    uint32_t height = 0;
+    check(sgx_spec_to_grey(spec.data(), T, n_mel, 1.0f, mx, mn, nullptr, 0, &height), "spec_to_grey size");
+    std::vector<float> grey((size_t)T * height);
+    check(sgx_spec_to_grey(spec.data(), T, n_mel, 1.0f, mx, mn, grey.data(), grey.size(), &height), "spec_to_grey");
+    const uint32_t nwidth = (uint32_t)(100 * (uint32_t)one_sec / sr); // bench.rs:91
+    std::vector<uint8_t> rgb((size_t)nwidth * 500 * 3);
+    bench_function("draw spectrogram", [&] {
+        check(sgx_grey_to_rgb(grey.data(), (uint32_t)T, height, nwidth, 500, 3, rgb.data(), rgb.size()), "grey_to_rgb");
+    });
+
+    sgx_multitrack *mt = nullptr;
+    check(sgx_mt_new(&mt), "MultiTrack::new");
+    const size_t ids[6] = {0, 1, 2, 3, 4, 5};
+    const float *pcm[6]; size_t ns[6]; uint32_t srs[6], chs[6];
+    for (int i = 0; i < 6; ++i) { pcm[i] = wav.data(); ns[i] = wav.size(); srs[i] = sr; chs[i] = 1; }
+    int changed = 0;
+    bench_function("add track", [&] { // bench.rs:35-44 (decoded PCM instead of re-reading the file six times)
+        check(sgx_mt_add_tracks_pcm(mt, ids, 6, pcm, ns, srs, chs, &changed), "add_tracks");
+    });
+    size_t need = 0;
+    check(sgx_mt_get_spec_image(mt, 0, 100.0f, 500, nullptr, 0, &need), "get_spec_image size");
+    std::vector<uint8_t> img(need);
+    bench_function("multitrack get spec image", [&] { // bench.rs:55-59
+        check(sgx_mt_get_spec_image(mt, 0, 100.0f, 500, img.data(), img.size(), &need), "get_spec_image");
+    });
+    sgx_mt_free(mt);
+    return 0;
+}

@@ -626,6 +626,25 @@ static int current_device()
     return d;
 }
 
+// Device buffers of the stage functions live per host thread and only ever grow: a call costs transfers and
+// launches, not cudaMalloc / cudaFree.
+struct StageWorkspace {
+    int device = -1;
+    TrackTables tt;
+    DevBuf<float> in, out, grey;
+    DevBuf<StftTrack> desc;
+    DevBuf<RenderTrack> rdesc;
+    DevBuf<uint8_t> pix;
+    AxisTableDev v, h;
+};
+static StageWorkspace &stage_workspace()
+{
+    thread_local StageWorkspace ws;
+    const int d = current_device();
+    if (ws.device != d) { ws = StageWorkspace(); ws.device = d; }
+    return ws;
+}
+
 StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t hop, size_t n_fft,
                     const float *window, const float *mel_fb, size_t n_mel, float *out, size_t cap_elems)
 {
@@ -643,14 +662,15 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     FftPlan &pl = ctx.plan(n_fft);
     std::vector<float> wbuf;
     if (!window) { wbuf.resize(win); calc_window(win, n_fft, wbuf.data()); window = wbuf.data(); } // lib.rs:403-408
-    TrackTables tt;
+    StageWorkspace &ws = stage_workspace();
+    TrackTables &tt = ws.tt;
     fill_tables(tt, win, n_fft, window, mode == MODE_MEL_DB ? mel_fb : nullptr, n_mel, pl.cfg, s);
-    DevBuf<float> d_in, d_out;
-    d_in.alloc(n + 16); d_out.alloc(elems);
+    DevBuf<float> &d_in = ws.in, &d_out = ws.out;
+    d_in.ensure(n + 16); d_out.ensure(elems);
     SGX_CUDA(cudaMemcpyAsync(d_in.p, input, n * sizeof(float), cudaMemcpyHostToDevice, s));
     StftTrack d = make_desc(d_in.p, PCM_F32, n, 1, win, hop, n_fft, (size_t)T, tt, d_out.p, n_out, nullptr);
     const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop);
-    DevBuf<StftTrack> dd; dd.upload(&d, 1, s);
+    DevBuf<StftTrack> &dd = ws.desc; dd.upload(&d, 1, s);
     StftLaunch L{};
     L.tracks = dd.p; L.n_tracks = 1;
     L.n_tiles = (int)(((size_t)T + tl.frames_per_tile - 1) / tl.frames_per_tile);
@@ -704,14 +724,15 @@ void stage_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint3
     const size_t need = (size_t)nwidth * nheight * channels;
     if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
     cudaStream_t s = 0;
-    DevBuf<float> dg; dg.alloc((size_t)width * height);
-    DevBuf<uint8_t> dout; dout.alloc(need);
+    StageWorkspace &ws = stage_workspace();
+    DevBuf<float> &dg = ws.grey; dg.ensure((size_t)width * height);
+    DevBuf<uint8_t> &dout = ws.pix; dout.ensure(need);
     SGX_CUDA(cudaMemcpyAsync(dg.p, grey, (size_t)width * height * sizeof(float), cudaMemcpyHostToDevice, s));
-    AxisTableDev v, h;
+    AxisTableDev &v = ws.v, &h = ws.h;
     v.taps = (std::max(16, (int)lanczos3_max_taps(height, nheight)) + 3) & ~3;
     h.taps = (std::max(16, (int)lanczos3_max_taps(width, nwidth)) + 3) & ~3;
-    v.left.alloc(nheight); v.cnt.alloc(nheight); v.sum.alloc(nheight); v.w.alloc((size_t)nheight * v.taps);
-    h.left.alloc(nwidth); h.cnt.alloc(nwidth); h.sum.alloc(nwidth); h.w.alloc((size_t)nwidth * h.taps);
+    v.left.ensure(nheight); v.cnt.ensure(nheight); v.sum.ensure(nheight); v.w.ensure((size_t)nheight * v.taps);
+    h.left.ensure(nwidth); h.cnt.ensure(nwidth); h.sum.ensure(nwidth); h.w.ensure((size_t)nwidth * h.taps);
     SGX_CUDA(launch_build_axis_table((int)height, (int)nheight, v.taps, false, v.left.p, v.cnt.p, v.sum.p, v.w.p, s));
     SGX_CUDA(launch_build_axis_table((int)width, (int)nwidth, h.taps, true, h.left.p, h.cnt.p, h.sum.p, h.w.p, s));
     RenderTrack r{};
@@ -720,7 +741,7 @@ void stage_grey_to_rgb(const float *grey, uint32_t width, uint32_t height, uint3
     r.nwidth = (int)nwidth; r.nheight = (int)nheight; r.out = dout.p;
     r.v_left = v.left.p; r.v_cnt = v.cnt.p; r.v_sum = v.sum.p; r.v_w = v.w.p; r.v_taps = v.taps;
     r.h_left = h.left.p; r.h_cnt = h.cnt.p; r.h_sum = h.sum.p; r.h_w = h.w.p; r.h_taps = h.taps;
-    DevBuf<RenderTrack> dr; dr.upload(&r, 1, s);
+    DevBuf<RenderTrack> &dr = ws.rdesc; dr.upload(&r, 1, s);
     const RenderTiling tl = plan_render_tiles((int)width, (int)height, (int)nwidth, (int)nheight);
     RenderLaunch L{};
     L.tracks = dr.p; L.n_tracks = 1; L.from_db = 0; L.range = nullptr; L.channels = channels;
