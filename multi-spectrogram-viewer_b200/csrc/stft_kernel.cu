@@ -92,17 +92,22 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsign
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    // try_wait suspends the thread for a hardware-defined time slice per attempt; a copy that never completes
+    // (it cannot, unless the descriptor table is corrupt) traps instead of hanging the GPU
+    for (unsigned spins = 0;; ++spins) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 26)) __trap();
+    }
 }
 
 // ---- sample access: channel sum + reflect (lib.rs:42, utils.rs:79-85) ---------------------------
