@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the spectrogram->RGBA path (BASELINE.json `metric`).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c3|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c3|c3s|c4 --n-fft F|c2|c1]
 
 A "step" is one pass of the hot path over one batch of synthetic PCM:
     MultiTrack.add_tracks (K1 fused analysis of every track -> dB, K2 global range incl. the
@@ -33,7 +33,7 @@ UNIT = "audio-s/s"
 PX_PER_SEC, NHEIGHT = 100.0, 500  # benches/bench.rs:57
 
 
-def workload(name):
+def workload(name, n_fft=2048):
     """Returns dict(sr, seconds, channels, tracks_per_gpu, settings kwargs, description)."""
     if name == "c5":
         return dict(sr=48000, seconds=600, channels=1, tracks=32, settings={}, seed=5005,
@@ -54,6 +54,10 @@ def workload(name):
                     settings=dict(n_mel=128),
                     desc="C2: six tracks of 44.032 s at 8/16/22.05/24/44.1/48 kHz (the reference's fixture rates, synthetic PCM), "
                          "per-rate W/hop/n_fft of lib.rs:43-46, 128-band mel, dB + RGBA 100 px/s x 500")
+    if name == "c4":  # one point of the long-window sweep; --n-fft picks F
+        return dict(sr=44100, seconds=600, channels=1, tracks=1, seed=4004,
+                    settings=dict(win_length=n_fft, hop_length=n_fft // 4, n_fft=n_fft, freq_scale=0),
+                    desc=f"C4: 10 min x 44.1 kHz mono, n_fft=W={n_fft} hop={n_fft // 4} Hann, linear-frequency dB + RGBA 100 px/s x 500")
     if name == "c1":
         return dict(sr=48000, seconds=44.031854, channels=1, tracks=1, seed=1001,
                     settings=dict(win_length=2048, hop_length=512, n_fft=2048, freq_scale=0),
@@ -447,7 +451,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c3s", "c2", "c1"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c3s", "c4", "c2", "c1"])
+    ap.add_argument("--n-fft", type=int, default=2048, help="FFT size of the c4 sweep point (512 ... 16384)")
     ap.add_argument("--tracks", type=int, default=0, help="override tracks per GPU (profiling runs only)")
     ap.add_argument("--seconds", type=float, default=0, help="override track length (profiling runs only)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -456,7 +461,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = workload(args.workload)
+    wl = workload(args.workload, args.n_fft)
     if args.tracks:
         wl["tracks"] = args.tracks; wl["desc"] += f" [OVERRIDE tracks={args.tracks}: not a headline run]"
     if args.seconds:

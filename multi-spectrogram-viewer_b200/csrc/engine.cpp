@@ -376,7 +376,13 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         const StftConfig &cfg = ctx_->plan(kv.first.first).cfg;
         int max_hop = 1;
         for (size_t id : kv.second) max_hop = std::max<int>(max_hop, (int)tracks_.at(id).hop);
-        Group g{kv.first.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop), 0};
+        int bank_floats = 0; // room the largest filterbank of the launch needs in shared memory
+        if (set_.freq_scale == SGX_FREQ_MEL)
+            for (size_t id : kv.second) {
+                const TrackTables &tt = *tracks_.at(id).tables;
+                bank_floats = std::max(bank_floats, ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel);
+            }
+        Group g{kv.first.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats), 0};
         g.tables = tracks_.at(kv.second.front()).tables;
         // a track id may appear twice in id_list; the last one wins, launch it once
         std::vector<size_t> uniq;
@@ -403,7 +409,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         L.tracks = d_stft_.p + g.first; L.n_tracks = (int)g.count; L.n_tiles = g.n_tiles;
         L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
         L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
-        L.tile_floats = g.tiling.tile_floats; L.tw = pl.tw.p; L.split = pl.split.p;
+        L.tile_floats = g.tiling.tile_floats; L.bank_floats = g.tiling.bank_floats; L.tw = pl.tw.p; L.split = pl.split.p;
         L.tw2 = pl.tw2.p; L.split_full = pl.split_full.p;
         L.mel_nnz = g.tables ? g.tables->mel_nnz : 0; L.mel_rows = g.tables ? (int)g.tables->n_mel : 0;
         if (!pipelined) { SGX_CUDA(launch_stft(pl.cfg, L, stream_)); continue; }
@@ -694,12 +700,13 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     d_in.ensure(n + 16); d_out.ensure(elems);
     SGX_CUDA(cudaMemcpyAsync(d_in.p, input, n * sizeof(float), cudaMemcpyHostToDevice, s));
     StftTrack d = make_desc(d_in.p, PCM_F32, n, 1, win, hop, n_fft, (size_t)T, tt, d_out.p, n_out, nullptr);
-    const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop);
+    const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop, mode == MODE_MEL_DB ? ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel : 0);
     DevBuf<StftTrack> &dd = ws.desc; dd.upload(&d, 1, s);
     StftLaunch L{};
     L.tracks = dd.p; L.n_tracks = 1;
     L.n_tiles = (int)(((size_t)T + tl.frames_per_tile - 1) / tl.frames_per_tile);
     L.mode = mode; L.frames_per_tile = tl.frames_per_tile; L.staged = tl.staged; L.tile_floats = tl.tile_floats;
+    L.bank_floats = tl.bank_floats;
     L.tw = pl.tw.p; L.split = pl.split.p;
     L.tw2 = pl.tw2.p; L.split_full = pl.split_full.p; L.mel_nnz = tt.mel_nnz; L.mel_rows = (int)tt.n_mel;
     SGX_CUDA(launch_stft(pl.cfg, L, s));

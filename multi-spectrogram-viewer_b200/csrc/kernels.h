@@ -28,8 +28,10 @@ size_t stft_max_dynamic_smem();
 cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &launch, cudaStream_t stream);
 
 // Chooses frames per tile / staging for a set of (hop) values sharing one FFT size.
-struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; };
-StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop);
+// `bank_floats`: shared-memory floats the largest mel filterbank of the launch needs (taps rounded up to 4, plus
+// 4 per filter for its descriptor), 0 when not a mel launch; the planner reports whether it got its own region.
+struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; };
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats = 0);
 
 // FFT twiddle tables for one size (host vectors -> caller uploads).
 void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);

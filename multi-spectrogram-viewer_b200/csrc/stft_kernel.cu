@@ -326,6 +326,44 @@ __host__ __device__ constexpr int last_radix(int h, int pts)
     return n > 1 ? n : pts;
 }
 
+// Where one CTA tile of a launch lives: its track, its frames and the PCM span they read.
+struct TileLoc {
+    int trk, t0, nfr, off0, len, len4;
+    long long S0, A0;
+    bool tma;
+};
+// `lo` is a lower bound of the track index (a CTA visits tiles, hence tracks, in rising order)
+__device__ __forceinline__ int find_track(const StftLaunch &L, int tile_id, int lo)
+{
+    int hi = L.n_tracks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (L.tracks[mid].tile_begin <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+// `td` may be the descriptor in global memory or the CTA's shared-memory copy of it
+__device__ __forceinline__ void locate_tile(const StftLaunch &L, int F, int tile_id, int trk, const StftTrack *td, TileLoc &o)
+{
+    o.trk = trk;
+    o.t0 = (tile_id - td->tile_begin) * L.frames_per_tile;
+    o.nfr = min(L.frames_per_tile, td->n_frames - o.t0);
+    const long long origin = td->origin;
+    o.S0 = (long long)(td->frame0 + o.t0) * td->hop - td->win / 2 - td->pad_l; // first (global) sample of the tile's first FFT frame
+    o.off0 = (int)((o.S0 - origin) & 3);
+    o.A0 = o.S0 - o.off0; // global index whose LOCAL position is 16-byte aligned: start of the staged tile
+    o.len = o.off0 + (o.nfr - 1) * td->hop + F;
+    o.len4 = (o.len + 3) & ~3;
+    // a tile that lies inside the track (no reflection), mono f32, 16-byte aligned: one TMA bulk copy
+    o.tma = L.staged && td->ch == 1 && td->fmt == PCM_F32 && ((reinterpret_cast<uintptr_t>(td->pcm) & 15) == 0) &&
+            o.A0 >= 0 && o.A0 + o.len4 <= td->n && o.A0 - origin >= 0 && o.A0 - origin + o.len4 <= td->avail;
+}
+__device__ __forceinline__ void issue_tile_copy(const StftTrack *td, const TileLoc &o, float *tile, unsigned long long *mbar)
+{
+    mbar_expect_tx(mbar, (unsigned)o.len4 * 4u);
+    bulk_copy_g2s(tile, reinterpret_cast<const float *>(td->pcm) + (o.A0 - td->origin), (unsigned)o.len4 * 4u, mbar);
+}
+
 template <int LOG2H, int PTS, int V, int G, int MC> struct K1Traits {
     static constexpr int H = 1 << LOG2H;
     static constexpr int NT = H / PTS;
@@ -342,63 +380,117 @@ stft_db_kernel(const StftLaunch L)
     using TR = K1Traits<LOG2H, PTS, V, G, MC>;
     constexpr int H = TR::H, NT = TR::NT, THREADS = TR::THREADS, PADH = TR::PADH, F = 2 * H;
     static_assert(NT >= 32 && (NT % 32) == 0, "a group must be whole warps");
+    static_assert(G <= 15, "one named barrier (1..15) per group");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
     float *tile = reinterpret_cast<float *>(smem_raw + 16);
     float *fftbuf = tile + L.tile_floats;
-    __shared__ float red_max[32], red_min[32];
 
     const int tid = threadIdx.x;
     const int grp = tid / NT, gt = tid % NT;
     float *sre = fftbuf + (size_t)grp * 2 * PADH * V;
     float *sim = sre + PADH * V;
 
-    // ---- which track / tile ---------------------------------------------------------------------
-    const int tile_id = blockIdx.x;
-    int lo = 0, hi = L.n_tracks - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (L.tracks[mid].tile_begin <= tile_id) lo = mid; else hi = mid - 1;
+    // ---- persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ------------------------------------
+    // The PCM tile is only read by the first FFT pass (into registers); as soon as every group has done
+    // that, thread 0 starts the bulk copy of the CTA's NEXT tile into the same buffer, so the copy runs
+    // under the remaining passes, the split and the mel projection of the current one.
+    float *bank = fftbuf + (size_t)G * 2 * PADH * V; // dedicated filterbank region (L.bank_floats floats), if any
+    const float *bank_src = nullptr;                  // whose taps it currently holds
+    const int mode = L.mode;
+    unsigned *done_cnt = reinterpret_cast<unsigned *>(smem_raw + 8); // warps that have consumed the current tile
+    if (L.staged) {
+        if (tid == 0) { mbar_init(mbar, 1); *done_cnt = 0u; }
+        __syncthreads();
     }
-    const StftTrack *__restrict__ td = L.tracks + lo;
+    unsigned phase = 0;
+    // The descriptor of the track the CTA is working on is kept in shared memory: finding a tile's place
+    // then costs a few shared loads instead of a chain of dependent global ones at every tile.
+    __shared__ StftTrack s_td;
+    __shared__ int s_trk, s_trk_end;
+    auto enter_track = [&](int tile_id, int lo) { // all threads
+        __syncthreads();
+        if (tid == 0) {
+            const int t = find_track(L, tile_id, lo);
+            s_trk = t;
+            s_trk_end = t + 1 < L.n_tracks ? L.tracks[t + 1].tile_begin : L.n_tiles;
+        }
+        __syncthreads();
+        const int *src = reinterpret_cast<const int *>(L.tracks + s_trk);
+        int *dst = reinterpret_cast<int *>(&s_td);
+        for (int i = tid; i < (int)(sizeof(StftTrack) / sizeof(int)); i += THREADS) dst[i] = src[i];
+        __syncthreads();
+    };
+    enter_track(blockIdx.x, 0);
+    int trk_end = s_trk_end;
+    const StftTrack *td = &s_td;
+    TileLoc cur;
+    locate_tile(L, F, blockIdx.x, s_trk, td, cur);
+    if (cur.tma && tid == 0) issue_tile_copy(td, cur, tile, mbar);
+
+    float vmax = -INFINITY, vmin = INFINITY;
+    int range_trk = -1;
+    // per-track extrema (lib.rs:197-200): flushed when the CTA moves on to another track
+    auto flush_range = [&]() {
+        if (range_trk < 0 || !(mode == MODE_LIN_DB || mode == MODE_MEL_DB)) return;
+        unsigned *slot = L.tracks[range_trk].range_slot;
+        if (slot == nullptr) return;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
+        }
+        if ((tid & 31) == 0 && vmax >= vmin) { // at least one value was produced
+            atomicMax(slot, enc_ordered(vmax));
+            atomicMin(slot + 1, enc_ordered(vmin));
+        }
+    };
+
+    for (int tile_id = blockIdx.x; tile_id < L.n_tiles; tile_id += gridDim.x) {
+    if (tile_id != (int)blockIdx.x) {
+        if (tile_id >= trk_end) { // uniform: the CTA moves on to another track
+            flush_range();
+            enter_track(tile_id, cur.trk);
+            trk_end = s_trk_end;
+        }
+        locate_tile(L, F, tile_id, s_trk, td, cur);
+    }
+    if (cur.trk != range_trk) { range_trk = cur.trk; vmax = -INFINITY; vmin = INFINITY; }
     const PcmView pv{td->pcm, td->n, td->ch, td->fmt, td->origin, td->avail};
-    const int win = td->win, hop = td->hop, pad_l = td->pad_l, T = td->n_frames;
+    const int hop = td->hop, T = td->n_frames;
     const float *__restrict__ win_f = td->win_f;
     float *__restrict__ out = td->out;
     const int n_out = td->n_out;
-    const int mode = L.mode;
-
-    const int t0 = (tile_id - td->tile_begin) * L.frames_per_tile;
-    const int nfr = min(L.frames_per_tile, T - t0);
-    const long long S0 = (long long)(td->frame0 + t0) * hop - win / 2 - pad_l; // first (global) sample of the tile's first FFT frame
-    const int off0 = (int)((S0 - pv.origin) & 3);
-    const long long A0 = S0 - off0; // global index whose LOCAL position is 16-byte aligned: start of the staged tile
+    const int t0 = cur.t0, nfr = cur.nfr, off0 = cur.off0;
+    const long long S0 = cur.S0;
     const bool vec_ok = ((hop | off0) & 1) == 0; // all frames of the tile start on an even float
+    (void)T;
 
-    // ---- stage the PCM tile ------------------------------------------------------------------------
+    // ---- filterbank of this track into its dedicated region (once per CTA and track) ----------------
+    if (mode == MODE_MEL_DB && L.bank_floats > 0 && td->mel_w != bank_src) {
+        __syncthreads(); // other groups may still be projecting frames of the previous track
+        const int nnz = __ldg(td->mel_cnt + 1);
+        const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo);
+        int4 *msm = reinterpret_cast<int4 *>(bank + ((nnz + 3) & ~3));
+        for (int i = tid; i < nnz; i += THREADS) bank[i] = __ldg(td->mel_w + i);
+        for (int i = tid; i < n_out; i += THREADS) msm[i] = __ldg(meta + i);
+        __syncthreads();
+        bank_src = td->mel_w;
+    }
+
+    // ---- the PCM tile: landed by TMA (issued one tile ago), or gathered here (edges, stereo, int16) -----
     if (L.staged) {
-        const int len = off0 + (nfr - 1) * hop + F;
-        const int len4 = (len + 3) & ~3;
-        const bool tma = pv.ch == 1 && pv.fmt == PCM_F32 &&
-                         ((reinterpret_cast<uintptr_t>(pv.pcm) & 15) == 0) && A0 >= 0 && A0 + len4 <= pv.n &&
-                         A0 - pv.origin >= 0 && A0 - pv.origin + len4 <= pv.avail;
-        if (tma) {
-            if (tid == 0) mbar_init(mbar, 1);
-            __syncthreads();
-            if (tid == 0) {
-                mbar_expect_tx(mbar, (unsigned)len4 * 4u);
-                bulk_copy_g2s(tile, reinterpret_cast<const float *>(pv.pcm) + (A0 - pv.origin),
-                              (unsigned)len4 * 4u, mbar);
-            }
-            mbar_wait(mbar, 0);
+        if (cur.tma) {
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
         } else {
-            for (int s = tid; s < len; s += THREADS) tile[s] = load_sample(pv, A0 + s);
+            __syncthreads(); // every group is past its first pass of the previous tile: the buffer is free
+            for (int s = tid; s < cur.len; s += THREADS) tile[s] = load_sample(pv, cur.A0 + s);
             __syncthreads();
         }
     }
 
-    float vmax = -INFINITY, vmin = INFINITY;
     const int iters = L.frames_per_tile / (G * V);
     for (int it = 0; it < iters; ++it) {
         if (it * G * V >= nfr) break; // uniform
@@ -438,6 +530,28 @@ stft_db_kernel(const StftLaunch L)
                         x0 = load_sample(pv, i); x1 = load_sample(pv, i + 1);
                     }
                     re[p][v] = x0 * w.x; im[p][v] = x1 * w.y;
+                }
+            }
+        }
+        // ---- the tile is in registers: let the next one stream in ---------------------------------------
+        // No CTA-wide barrier: every warp checks in on a shared counter once its loads of the tile have
+        // been performed, and the warp that checks in last starts the copy.  The groups keep drifting
+        // against each other, which is what hides their barrier and shared-memory latencies.
+        if (L.staged && (it == iters - 1 || (it + 1) * G * V >= nfr)) {
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                __threadfence_block();
+                const unsigned seen = atomicAdd(done_cnt, 1u);
+                if (seen % (THREADS / 32) == THREADS / 32 - 1) {
+                    const int nt = tile_id + (int)gridDim.x;
+                    if (nt < L.n_tiles) {
+                        TileLoc nx;
+                        const StftTrack *ntd = td;
+                        int ntrk = cur.trk;
+                        if (nt >= trk_end) { ntrk = find_track(L, nt, cur.trk); ntd = L.tracks + ntrk; }
+                        locate_tile(L, F, nt, ntrk, ntd, nx);
+                        if (nx.tma) issue_tile_copy(ntd, nx, tile, mbar);
+                    }
                 }
             }
         }
@@ -620,13 +734,14 @@ stft_db_kernel(const StftLaunch L)
             constexpr int NWARPS = NT / 32;
             const int *__restrict__ sched = td->mel_cnt; // {slots, taps, staged, 0, block ids [slots][NWARPS]}
             const int nslots = __ldg(sched), nnz = __ldg(sched + 1);
-            const bool staged = __ldg(sched + 2) != 0;
+            const bool staged = L.bank_floats > 0 || __ldg(sched + 2) != 0;
             const int lg = td->mel_log2p, P = 1 << lg;
             const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo); // {lo, cnt, off, 0}
             const float *__restrict__ mw = td->mel_w;
-            float *wsm = sim;
-            int4 *msm = reinterpret_cast<int4 *>(sim + ((nnz + 3) & ~3));
-            if (staged) {
+            const bool dedicated = L.bank_floats > 0; // taps already sit in the CTA's filterbank region
+            float *wsm = dedicated ? bank : sim;
+            int4 *msm = reinterpret_cast<int4 *>(wsm + ((nnz + 3) & ~3));
+            if (staged && !dedicated) {
                 if constexpr (!FUSED) group_sync<G, NT>(grp); // split pairs of other threads still read sim
                 for (int i = gt; i < nnz; i += NT) wsm[i] = __ldg(mw + i);
                 for (int i = gt; i < n_out; i += NT) msm[i] = __ldg(meta + i);
@@ -679,23 +794,8 @@ stft_db_kernel(const StftLaunch L)
         group_sync<G, NT>(grp); // spectrum / magnitudes consumed before the next iteration overwrites the buffer
     }
 
-    // ---- per-track extrema (lib.rs:197-200) ----------------------------------------------------------
-    if (td->range_slot != nullptr && (mode == MODE_LIN_DB || mode == MODE_MEL_DB)) {
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
-            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
-        }
-        if ((tid & 31) == 0) { red_max[tid >> 5] = vmax; red_min[tid >> 5] = vmin; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < THREADS / 32; ++w) { vmax = fmaxf(vmax, red_max[w]); vmin = fminf(vmin, red_min[w]); }
-            if (vmax >= vmin) { // at least one value was produced
-                atomicMax(td->range_slot, enc_ordered(vmax));
-                atomicMin(td->range_slot + 1, enc_ordered(vmin));
-            }
-        }
-    }
+    } // tiles of this CTA
+    flush_range();
 }
 
 // =====================================================================================================
@@ -1003,6 +1103,14 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, i
     }
 }
 
+int resident_sms()
+{
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
 template <int LOG2H, int PTS, int V, int G, int MC>
 cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
@@ -1010,7 +1118,9 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
     auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC>;
     cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     if (e != cudaSuccess) return e;
-    kern<<<L.n_tiles, TR::THREADS, smem, stream>>>(L);
+    // persistent CTAs: as many as are resident at once, each walking tiles blockIdx.x + k gridDim.x
+    const int grid = std::min(L.n_tiles, resident_sms() * MC);
+    kern<<<grid, TR::THREADS, smem, stream>>>(L);
     count_launch();
     return cudaGetLastError();
 }
@@ -1025,9 +1135,12 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 #define SGX_K1_TABLE(X) \
     X(8, 8, 4, 8, 2)    \
     X(9, 8, 4, 4, 2)    \
+    X(9, 8, 4, 8, 1)    \
+    X(10, 8, 4, 4, 1)   \
     X(10, 8, 4, 2, 2)   \
     X(10, 8, 2, 2, 3)   \
     X(10, 4, 4, 1, 4)   \
+    X(11, 8, 4, 2, 1)   \
     X(11, 8, 4, 1, 2)   \
     X(12, 8, 4, 1, 1)   \
     X(13, 8, 2, 1, 1)
@@ -1073,7 +1186,7 @@ size_t stft_warp_smem_bytes(int nnz, int n_mel) { return k1w_smem_bytes(nnz, n_m
 
 size_t stft_max_dynamic_smem() { return 227 * 1024; }
 
-StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop)
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats)
 {
     StftTiling t{};
     if (cfg.warp_per_frame) { // one "tile" per frame; nothing is staged per tile
@@ -1091,25 +1204,35 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop)
     const int ctas = cfg.min_ctas > 0 ? cfg.min_ctas : 1;
     size_t budget = (size_t)(228 * 1024) / ctas - 1024 - 512;
     if (budget > stft_max_dynamic_smem()) budget = stft_max_dynamic_smem();
-    const size_t avail = budget > cfg.fft_smem + 16 ? budget - cfg.fft_smem - 16 : 0;
-    const long cap_floats = (long)(avail / sizeof(float));
     int want_nfr = 0;
     if (const char *e = getenv("SGX_K1_NFR")) want_nfr = atoi(e);
-    // floats(nfr) = 3 + (nfr-1)*hop + F, rounded up to 4
-    int best = 0;
-    for (int mult = 1; mult <= 8; ++mult) {
-        const int nfr = unit * mult;
-        const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
-        if (need <= cap_floats && (want_nfr == 0 || nfr <= want_nfr || best == 0)) best = nfr;
+    static const bool no_bank = getenv("SGX_K1_NOBANK") && atoi(getenv("SGX_K1_NOBANK")) == 1;
+    if (no_bank) bank_floats = 0;
+    // First choice: the filterbank of a track gets its own region (loaded once per persistent CTA and
+    // track) next to a staged tile of at least one round of frames; if that does not fit, the taps are
+    // staged per round in the dead imaginary plane (or read through L1), as the mel schedule says.
+    for (int with_bank = bank_floats > 0 ? 1 : 0; with_bank >= 0; --with_bank) {
+        const size_t fixed = cfg.fft_smem + 16 + (with_bank ? (size_t)bank_floats * sizeof(float) : 0);
+        const long cap_floats = budget > fixed ? (long)((budget - fixed) / sizeof(float)) : 0;
+        // floats(nfr) = 3 + (nfr-1)*hop + F, rounded up to 4
+        int best = 0;
+        for (int mult = 1; mult <= 8; ++mult) {
+            const int nfr = unit * mult;
+            const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
+            if (need <= cap_floats && (want_nfr == 0 || nfr <= want_nfr || best == 0)) best = nfr;
+        }
+        if (best == 0 && with_bank) continue; // rather stage the tile than the taps
+        t.bank_floats = with_bank ? bank_floats : 0;
+        if (best == 0) {
+            t.frames_per_tile = unit; t.staged = 0; t.tile_floats = 0;
+        } else {
+            t.frames_per_tile = best; t.staged = 1;
+            long need = 3 + (long)(best - 1) * max_hop + cfg.n_fft;
+            t.tile_floats = (int)((need + 3) & ~3L) + 4;
+        }
+        break;
     }
-    if (best == 0) {
-        t.frames_per_tile = unit; t.staged = 0; t.tile_floats = 0;
-    } else {
-        t.frames_per_tile = best; t.staged = 1;
-        long need = 3 + (long)(best - 1) * max_hop + cfg.n_fft;
-        t.tile_floats = (int)((need + 3) & ~3L) + 4;
-    }
-    t.smem_bytes = 16 + (size_t)t.tile_floats * sizeof(float) + cfg.fft_smem;
+    t.smem_bytes = 16 + (size_t)(t.tile_floats + t.bank_floats) * sizeof(float) + cfg.fft_smem;
     return t;
 }
 
@@ -1157,7 +1280,7 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t
         return cudaGetLastError();
     }
     const size_t smem = cfg.generic ? cfg.fft_smem
-                                    : 16 + (size_t)L.tile_floats * sizeof(float) + cfg.fft_smem;
+                                    : 16 + (size_t)(L.tile_floats + L.bank_floats) * sizeof(float) + cfg.fft_smem;
     if (cfg.generic) {
         cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(stft_generic_kernel), smem);
         if (e != cudaSuccess) return e;

@@ -1,0 +1,23 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() {
+  name=$1; shift
+  env "$@" > gpurun_out/s_$name.log 2> gpurun_out/s_$name.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/s_$name.log").read().strip().splitlines()[-1]); r=d["roofline_step"]
+    print("%-22s step %.3f ms  k1 %.3f ms  k3 %.3f ms  value %.0f" % ("$name", d["ms_per_step"], r["k1_ms"], r["k3_ms"], d["value"]))
+except Exception as ex:
+    print("$name failed", ex); print(open("gpurun_out/s_$name.err").read()[-600:])
+PY
+}
+B="timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu --no-e2e"
+run c2 X=1 $B --workload c2
+run c2_nobank SGX_K1_NOBANK=1 $B --workload c2
+run c2b X=1 $B --workload c2
+run c2b_nobank SGX_K1_NOBANK=1 $B --workload c2
+run c3 X=1 $B --workload c3
+run c3_nfr16 SGX_K1_NFR=16 $B --workload c3
+run c3_nfr24 SGX_K1_NFR=24 $B --workload c3
+run c5 X=1 $B --workload c5
