@@ -9,6 +9,9 @@
 // The grey image and the vertically resampled intermediate only ever exist as shared-memory
 // tiles; HBM sees one read of dB and one write of pixels.
 #include <cstdint>
+#include <cmath>
+#include <cstdlib>
+#include <type_traits>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -89,6 +92,14 @@ __device__ __forceinline__ float sinc_dev(float t)
 __device__ __forceinline__ float lanczos3_dev(float x)
 {
     return fabsf(x) < 3.0f ? __fmul_rn(sinc_dev(x), sinc_dev(__fdiv_rn(x, 3.0f))) : 0.0f;
+}
+
+// upper bound of the taps one output index has: (r - l) of the table builder below
+__host__ __device__ inline int lanczos3_taps_bound(int n_in, int n_out)
+{
+    const float ratio = (float)n_in / (float)n_out;
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    return (int)(2.0f * 3.0f * sratio) + 3;
 }
 
 __global__ void build_axis_table_kernel(int n_in, int n_out, int taps, int tap_major, int *left_o,
@@ -452,6 +463,209 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K3 wide path: any number of taps per axis, as long as the source window of one tile fits in shared
+// memory (strong minification on either axis: short FFTs at 100 px/s, long FFTs at 500 rows).  Same
+// three phases and layouts as the fast path, with the tap loops running over the tables:
+//   B  a warp owns output rows and its lanes run along the frames (up to 4 frames per lane), so the
+//      weight of a tap is one uniform 128-bit load per 4 taps and the grey loads are conflict-free
+//      whatever the vertical ratio is,
+//   C  lane <-> output column, weights read tap-major (coalesced), every 128-bit shared load brings one
+//      source frame of four output rows, up to 4 row quads per lane share a weight load.
+// Taps are summed in ascending order into one accumulator per output and divided by the weight sum
+// afterwards, as the reference's resize does; the rows beyond an index's own tap count hold zero weights.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWideMaxSmem = 200 * 1024;
+__host__ __device__ constexpr int wide_pitch(int n) // multiple of 4 whose quarter is odd, >= n
+{
+    int q = (n + 3) / 4;
+    if ((q & 1) == 0) ++q;
+    return q * 4;
+}
+
+template <bool FROM_DB, int CH>
+__global__ void __launch_bounds__(kRenderThreads) render_wide_kernel(const RenderLaunch L)
+{
+    const int RCAP = L.rv_max, GP = L.fc; // G [row][frame], pitch = frame capacity
+    extern __shared__ __align__(16) float rsm[];
+    __shared__ float2 cmab[27];
+    float *G = rsm;
+    float *Tm = rsm + (size_t)RCAP * GP;  // [frame][out row]
+    const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
+    const int nwidth = tr->nwidth, nheight = tr->nheight;
+    const int ox_begin = tr->ox_begin, ox_count = tr->ox_count, frame0 = tr->frame0, src_frames = tr->src_frames;
+    const int ox_end = ox_begin + ox_count; // this launch renders columns [ox_begin, ox_end)
+    const int ox0 = ox_begin + blockIdx.x * L.px, oy0 = blockIdx.y * L.py;
+    if (ox0 >= ox_end || oy0 >= nheight) return;
+    const int pxc = min(L.px, ox_end - ox0), pyc = min(L.py, nheight - oy0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3], (float)kColormap[tid / 3 + 1][tid % 3]);
+
+    const int *__restrict__ h_left = tr->h_left;
+    const int *__restrict__ v_left = tr->v_left;
+    const float *__restrict__ src = tr->src;
+    const int width = tr->width, height = tr->height, n_out = tr->n_out;
+    const int v_taps = tr->v_taps;
+    // taps an index can really have (the tables are at least 16 wide for the fast path; the rest is zeros)
+    const int h_need = min(tr->h_taps, lanczos3_taps_bound(width, nwidth));
+    const int v_need = min(v_taps, (lanczos3_taps_bound(height, nheight) + 3) & ~3);
+
+    const int fl = __ldg(h_left + ox0);
+    const int nfr = min(__ldg(h_left + ox0 + pxc - 1) + h_need - fl, GP);
+    const int nfq = (nfr + 3) >> 2;                 // frame quads
+    const int yl = __ldg(v_left + oy0);
+    const int nrow = min(__ldg(v_left + oy0 + pyc - 1) + v_need - yl, RCAP);
+
+    // ---- A: grey tile ---------------------------------------------------------------------------------
+    float min_db = 0.0f, inv_span = 0.0f;
+    if (FROM_DB) { min_db = L.range[1]; inv_span = __frcp_rn(L.range[0] - L.range[1]); }
+    const int pad_rows = FROM_DB ? height - n_out : 0;
+    const int yy_lo = max(pad_rows - yl, 0), yy_hi = min(height - yl, nrow);
+    if (FROM_DB && nfq < kRenderThreads / 32) {
+        // few frames, many rows (strong vertical minification): a warp reads 32 consecutive rows of ONE frame
+        // -- they are contiguous in the dB array -- so that every warp has loads in flight
+        const int nblk = (nrow + 32 * kABatch - 1) / (32 * kABatch);
+        for (int item = warp; item < nfq * 4 * nblk; item += kRenderThreads / 32) {
+            const int fx = item / nblk, j0 = (item - fx * nblk) * 32 * kABatch;
+            const int f = fl + fx, lf = f - frame0;
+            const bool fok = f < width && lf >= 0 && lf < src_frames;
+            const float *__restrict__ p0 = src + (size_t)(fok ? lf : 0) * n_out + (height - 1 - yl - lane);
+            float v[kABatch];
+#pragma unroll
+            for (int j = 0; j < kABatch; ++j) {
+                const int yy = j0 + j * 32 + lane;
+                v[j] = -INFINITY; // -inf -> grey 0 after the saturate
+                if (fok && yy >= yy_lo && yy < yy_hi) v[j] = __ldg(p0 - (j0 + j * 32));
+            }
+#pragma unroll
+            for (int j = 0; j < kABatch; ++j) {
+                const int yy = j0 + j * 32 + lane;
+                if (yy < nrow) G[yy * GP + fx] = __saturatef((v[j] - min_db) * inv_span);
+            }
+        }
+    } else {
+        // as in the fast path: a warp loads 8 rows x 4 frames per request
+        const int fsub = lane & 3, rsub = lane >> 2;
+        for (int fq = warp; fq < nfq; fq += kRenderThreads / 32) {
+            const int fx = fq * 4 + fsub;
+            const int f = fl + fx;
+            const int lf = FROM_DB ? f - frame0 : f; // row of the (possibly time-sliced) dB array
+            const bool fok = f < width && lf >= 0 && (!FROM_DB || lf < src_frames);
+            const float *__restrict__ p0 = FROM_DB ? src + (size_t)(fok ? lf : 0) * n_out + (height - 1 - yl - rsub)
+                                                   : src + (size_t)(yl + rsub) * width + (fok ? f : 0);
+            float *g0 = G + rsub * GP + fx;
+            for (int j0 = 0; j0 < nrow; j0 += 8 * kABatch) {
+                float v[kABatch];
+#pragma unroll
+                for (int j = 0; j < kABatch; ++j) {
+                    const int yy = j0 + j * 8 + rsub;
+                    const bool ok = fok && yy >= yy_lo && yy < yy_hi;
+                    v[j] = FROM_DB ? -INFINITY : 0.0f; // -inf -> grey 0 after the saturate
+                    if (ok) v[j] = FROM_DB ? __ldg(p0 - (j0 + j * 8)) : __ldg(p0 + (size_t)(j0 + j * 8) * width);
+                }
+#pragma unroll
+                for (int j = 0; j < kABatch; ++j) {
+                    const int yy = j0 + j * 8 + rsub;
+                    const float g = FROM_DB ? __saturatef((v[j] - min_db) * inv_span) : v[j];
+                    if (yy < RCAP) g0[(j0 + j * 8) * GP] = g;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- B: vertical pass: warp <-> output row, lanes <-> frames ----------------------------------------
+    {
+        const int *__restrict__ v_cnt = tr->v_cnt;
+        const float *__restrict__ v_sum = tr->v_sum;
+        const int nfx = nfq * 4;
+        auto rows = [&](auto na_tag) {
+            constexpr int NA = decltype(na_tag)::value; // frames per lane
+            for (int oyl = warp; oyl < pyc; oyl += kRenderThreads / 32) {
+                const int oy = oy0 + oyl;
+                const int voff = __ldg(v_left + oy) - yl;
+                const int cnt4 = (__ldg(v_cnt + oy) + 3) >> 2;
+                const float vs = __ldg(v_sum + oy);
+                const float4 *__restrict__ wrow = reinterpret_cast<const float4 *>(tr->v_w + (size_t)oy * v_taps);
+                for (int fb = 0; fb < nfx; fb += 32 * NA) {
+                    const float *g[NA];
+                    float t[NA];
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) { g[a] = G + voff * GP + min(fb + a * 32 + lane, nfx - 1); t[a] = 0.0f; }
+                    for (int i4 = 0; i4 < cnt4; ++i4) {
+                        const float4 w = __ldg(wrow + i4);
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) {
+                            const float *gp = g[a] + (i4 * 4) * GP;
+                            const float g0 = gp[0], g1 = gp[GP], g2 = gp[2 * GP], g3 = gp[3 * GP];
+                            t[a] = fmaf(g0, w.x, t[a]); t[a] = fmaf(g1, w.y, t[a]);
+                            t[a] = fmaf(g2, w.z, t[a]); t[a] = fmaf(g3, w.w, t[a]);
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) {
+                        const int fx = fb + a * 32 + lane;
+                        if (fx < nfx) Tm[fx * kFpTP + oyl] = clamp_pos(__fdiv_rn(t[a], vs));
+                    }
+                }
+            }
+        };
+        if (nfx <= 32) rows(std::integral_constant<int, 1>{});
+        else if (nfx <= 64) rows(std::integral_constant<int, 2>{});
+        else rows(std::integral_constant<int, 4>{});
+    }
+    __syncthreads();
+
+    // ---- C: horizontal pass, colour, store -----------------------------------------------------------------
+    for (int cb = 0; cb < pxc; cb += kFpTile) { // 64-column blocks of the tile
+        const int oxl = cb + (warp & 1) * 32 + lane;
+        const int ox = ox0 + min(oxl, pxc - 1);
+        const int hoff = __ldg(h_left + ox) - fl;
+        const int cnt = __reduce_max_sync(0xffffffffu, __ldg(tr->h_cnt + ox)); // zero weights beyond a lane's own count
+        const float hs = __ldg(tr->h_sum + ox);
+        const float *__restrict__ wcol = tr->h_w + ox; // tap-major: tap i of column ox at wcol[i * nwidth]
+        const float *t_in = Tm + hoff * kFpTP;
+        unsigned char *__restrict__ outp = tr->out;
+        const int nrq = (pyc + 3) >> 2;
+        // this lane's row quads: (warp >> 1) + 4 k, k < 4 (a tile is at most 64 rows = 16 quads)
+        float t[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[k][j] = 0.0f;
+        const int rq0 = warp >> 1;
+        for (int i = 0; i < cnt; ++i) {
+            const float w = __ldg(wcol + (size_t)i * nwidth);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rq = rq0 + 4 * k;
+                if (rq < nrq) {
+                    const float4 v = *reinterpret_cast<const float4 *>(t_in + i * kFpTP + rq * 4);
+                    t[k][0] = fmaf(v.x, w, t[k][0]); t[k][1] = fmaf(v.y, w, t[k][1]);
+                    t[k][2] = fmaf(v.z, w, t[k][2]); t[k][3] = fmaf(v.w, w, t[k][3]);
+                }
+            }
+        }
+        if (oxl < pxc) {
+            const int opitch = ox_count;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rq = rq0 + 4 * k;
+                if (rq >= nrq) continue;
+                size_t pix = (size_t)(oy0 + rq * 4) * opitch + (ox - ox_begin);
+#pragma unroll
+                for (int j = 0; j < 4; ++j, pix += opitch) {
+                    if (rq * 4 + j < pyc) {
+                        const unsigned c = grey_to_rgba_fast(clamp_pos(__fdiv_rn(t[k][j], hs)), cmab);
+                        if (CH == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
+                        else { outp[pix * 3] = (unsigned char)c; outp[pix * 3 + 1] = (unsigned char)(c >> 8); outp[pix * 3 + 2] = (unsigned char)(c >> 16); }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // display.rs:44-54 as a stand-alone stage (surface 2)
 __global__ void spec_to_grey_kernel(const float *__restrict__ spec, int T, int n_out, int height,
                                     float max_db, float min_db, float *__restrict__ grey)
@@ -560,12 +774,7 @@ cudaError_t launch_range_commit(const float *max_negmin, float db_range, float *
     return cudaGetLastError();
 }
 
-uint32_t lanczos3_max_taps(uint32_t n_in, uint32_t n_out)
-{
-    const float ratio = (float)n_in / (float)n_out;
-    const float sratio = ratio < 1.0f ? 1.0f : ratio;
-    return (uint32_t)(2.0f * 3.0f * sratio) + 3;
-}
+uint32_t lanczos3_max_taps(uint32_t n_in, uint32_t n_out) { return (uint32_t)lanczos3_taps_bound((int)n_in, (int)n_out); }
 
 cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_major, int *left,
                                     int *cnt, float *sum, float *w, cudaStream_t s)
@@ -586,6 +795,25 @@ RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
         t.px = kFpTile; t.py = kFpTile; t.fc = fp_cap(th); t.rv_max = fp_cap(tv); t.smem_bytes = fp_smem(tv, th);
         t.fast = tv * 100 + th;
         return t;
+    }
+    // wide path: runtime tap counts, the whole source window of a px x py tile in shared memory.  Under
+    // horizontal magnification a tile is made wider, so that the frames it owns outnumber the Lanczos halo
+    // (otherwise most of the vertical pass would be repeated by the neighbouring tiles).
+    {
+        const int vt = (lanczos3_taps_bound(height, nheight) + 3) & ~3;
+        const int ht = lanczos3_taps_bound(width, nwidth);
+        const int px = rhf <= 0.25f ? 4 * kFpTile : (rhf <= 0.5f ? 2 * kFpTile : kFpTile);
+        const int gp = wide_pitch((int)std::ceil((px - 1) * (double)rhf) + ht + 2);
+        RenderTiling pick{};
+        for (int py = kFpTile; py >= 16; py >>= 1) {
+            const int rcap = ((int)std::ceil((py - 1) * (double)rvf) + vt + 2 + 7) & ~7;
+            const size_t smem = ((size_t)rcap * gp + (size_t)gp * kFpTP) * sizeof(float);
+            if (smem > (size_t)kWideMaxSmem) continue;
+            if (pick.fast == 0) pick = RenderTiling{px, py, gp, rcap, smem, 1};
+            if (smem <= 113 * 1024) { pick = RenderTiling{px, py, gp, rcap, smem, 1}; break; } // two CTAs per SM
+        }
+        static const bool no_wide = getenv("SGX_K3_NOWIDE") && atoi(getenv("SGX_K3_NOWIDE")) == 1;
+        if (pick.fast == 1 && !no_wide) return pick;
     }
     // frames a tile of px output columns needs, rows a tile of py output rows needs
     const double rh = (double)width / nwidth, rv = (double)height / nheight;
@@ -626,6 +854,23 @@ cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight
                           int fast, cudaStream_t s)
 {
     if (L.n_tracks <= 0 || max_nwidth <= 0 || max_nheight <= 0) return cudaSuccess;
+    if (fast == 1) { // wide path: tile L.px x L.py, capacities in L.fc / L.rv_max
+        dim3 grid((max_nwidth + L.px - 1) / L.px, (max_nheight + L.py - 1) / L.py, L.n_tracks);
+        cudaError_t err = cudaErrorInvalidValue;
+#define SGX_WIDE(DB, CHN)                                                                                     \
+        if ((L.from_db != 0) == DB && L.channels == CHN) {                                                    \
+            auto kern = render_wide_kernel<DB, CHN>;                                                          \
+            cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem_bytes);           \
+            if (e != cudaSuccess) return e;                                                                   \
+            kern<<<grid, kRenderThreads, smem_bytes, s>>>(L);                                                 \
+            err = cudaSuccess;                                                                                \
+        }
+        SGX_WIDE(true, 4) SGX_WIDE(true, 3) SGX_WIDE(false, 4) SGX_WIDE(false, 3)
+#undef SGX_WIDE
+        if (err != cudaSuccess) return err;
+        count_launch();
+        return cudaGetLastError();
+    }
     if (fast) {
         dim3 grid((max_nwidth + kFpTile - 1) / kFpTile, (max_nheight + kFpTile - 1) / kFpTile, L.n_tracks);
         const int tv = fast / 100, th = fast % 100;

@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 -k "render or geometry or image or wav or slice or golden or grey" > gpurun_out/pytest_k3.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k3.log
+tail -3 gpurun_out/pytest_k3.log
 run() {
   name=$1; shift
   env "$@" > gpurun_out/s_$name.log 2> gpurun_out/s_$name.err
@@ -12,12 +14,7 @@ except Exception as ex:
     print("$name failed", ex); print(open("gpurun_out/s_$name.err").read()[-600:])
 PY
 }
-B="timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu --no-e2e"
-run c2 X=1 $B --workload c2
-run c2_nobank SGX_K1_NOBANK=1 $B --workload c2
-run c2b X=1 $B --workload c2
-run c2b_nobank SGX_K1_NOBANK=1 $B --workload c2
-run c3 X=1 $B --workload c3
-run c3_nfr16 SGX_K1_NFR=16 $B --workload c3
-run c3_nfr24 SGX_K1_NFR=24 $B --workload c3
-run c5 X=1 $B --workload c5
+B="timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu --no-e2e"
+for F in 512 4096 8192 16384; do
+  run c4_${F} X=1 $B --workload c4 --n-fft $F --tracks 4
+done
