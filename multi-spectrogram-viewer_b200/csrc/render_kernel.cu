@@ -143,6 +143,9 @@ __device__ __forceinline__ float clamp_pos(float v)
     return v < 0.0f ? 0.0f : (v > 3.4028235e38f ? 3.4028235e38f : v);
 }
 
+// the same clamp for values that cannot be NaN (sums of finite products): branch-free
+__device__ __forceinline__ float clamp_fin(float v) { return fminf(fmaxf(v, 0.0f), 3.4028235e38f); }
+
 // display.rs:24-42 convert_grey_to_color; cm = colour map as floats in shared memory
 __device__ __forceinline__ uchar4 grey_to_color(float x, const float *cm)
 {
@@ -484,13 +487,14 @@ __host__ __device__ constexpr int wide_pitch(int n) // multiple of 4 whose quart
 }
 
 template <bool FROM_DB, int CH>
-__global__ void __launch_bounds__(kRenderThreads) render_wide_kernel(const RenderLaunch L)
+__global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const RenderLaunch L)
 {
     const int RCAP = L.rv_max, GP = L.fc; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
     __shared__ float2 cmab[27];
     float *G = rsm;
-    float *Tm = rsm + (size_t)RCAP * GP;  // [frame][out row]
+    float *Tm = rsm + (size_t)RCAP * GP;  // [frame][out row], pitch TP
+    const int TP = L.py + 4;              // 68 / 36 / 20: multiples of 4 with an odd quarter
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
     const int nwidth = tr->nwidth, nheight = tr->nheight;
     const int ox_begin = tr->ox_begin, ox_count = tr->ox_count, frame0 = tr->frame0, src_frames = tr->src_frames;
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_wide_kernel(const Rende
                 const int oy = oy0 + oyl;
                 const int voff = __ldg(v_left + oy) - yl;
                 const int cnt4 = (__ldg(v_cnt + oy) + 3) >> 2;
-                const float vs = __ldg(v_sum + oy);
+                const float rvs = __frcp_rn(__ldg(v_sum + oy));
                 const float4 *__restrict__ wrow = reinterpret_cast<const float4 *>(tr->v_w + (size_t)oy * v_taps);
                 for (int fb = 0; fb < nfx; fb += 32 * NA) {
                     const float *g[NA];
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_wide_kernel(const Rende
 #pragma unroll
                     for (int a = 0; a < NA; ++a) {
                         const int fx = fb + a * 32 + lane;
-                        if (fx < nfx) Tm[fx * kFpTP + oyl] = clamp_pos(__fdiv_rn(t[a], vs));
+                        if (fx < nfx) Tm[fx * TP + oyl] = clamp_fin(t[a] * rvs);
                     }
                 }
             }
@@ -622,9 +626,9 @@ __global__ void __launch_bounds__(kRenderThreads) render_wide_kernel(const Rende
         const int ox = ox0 + min(oxl, pxc - 1);
         const int hoff = __ldg(h_left + ox) - fl;
         const int cnt = __reduce_max_sync(0xffffffffu, __ldg(tr->h_cnt + ox)); // zero weights beyond a lane's own count
-        const float hs = __ldg(tr->h_sum + ox);
+        const float rhs = __frcp_rn(__ldg(tr->h_sum + ox));
         const float *__restrict__ wcol = tr->h_w + ox; // tap-major: tap i of column ox at wcol[i * nwidth]
-        const float *t_in = Tm + hoff * kFpTP;
+        const float *t_in = Tm + hoff * TP;
         unsigned char *__restrict__ outp = tr->out;
         const int nrq = (pyc + 3) >> 2;
         // this lane's row quads: (warp >> 1) + 4 k, k < 4 (a tile is at most 64 rows = 16 quads)
@@ -634,18 +638,24 @@ __global__ void __launch_bounds__(kRenderThreads) render_wide_kernel(const Rende
 #pragma unroll
             for (int j = 0; j < 4; ++j) t[k][j] = 0.0f;
         const int rq0 = warp >> 1;
-        for (int i = 0; i < cnt; ++i) {
-            const float w = __ldg(wcol + (size_t)i * nwidth);
+        auto tap = [&](int i, float w) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int rq = rq0 + 4 * k;
                 if (rq < nrq) {
-                    const float4 v = *reinterpret_cast<const float4 *>(t_in + i * kFpTP + rq * 4);
+                    const float4 v = *reinterpret_cast<const float4 *>(t_in + i * TP + rq * 4);
                     t[k][0] = fmaf(v.x, w, t[k][0]); t[k][1] = fmaf(v.y, w, t[k][1]);
                     t[k][2] = fmaf(v.z, w, t[k][2]); t[k][3] = fmaf(v.w, w, t[k][3]);
                 }
             }
+        };
+        int i = 0;
+        for (; i + 4 <= cnt; i += 4) { // four weight loads in flight before the first use
+            const float w0 = __ldg(wcol + (size_t)i * nwidth), w1 = __ldg(wcol + (size_t)(i + 1) * nwidth);
+            const float w2 = __ldg(wcol + (size_t)(i + 2) * nwidth), w3 = __ldg(wcol + (size_t)(i + 3) * nwidth);
+            tap(i, w0); tap(i + 1, w1); tap(i + 2, w2); tap(i + 3, w3);
         }
+        for (; i < cnt; ++i) tap(i, __ldg(wcol + (size_t)i * nwidth));
         if (oxl < pxc) {
             const int opitch = ox_count;
 #pragma unroll
@@ -656,7 +666,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_wide_kernel(const Rende
 #pragma unroll
                 for (int j = 0; j < 4; ++j, pix += opitch) {
                     if (rq * 4 + j < pyc) {
-                        const unsigned c = grey_to_rgba_fast(clamp_pos(__fdiv_rn(t[k][j], hs)), cmab);
+                        const unsigned c = grey_to_rgba_fast(clamp_fin(t[k][j] * rhs), cmab);
                         if (CH == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
                         else { outp[pix * 3] = (unsigned char)c; outp[pix * 3 + 1] = (unsigned char)(c >> 8); outp[pix * 3 + 2] = (unsigned char)(c >> 16); }
                     }
@@ -802,15 +812,24 @@ RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
     {
         const int vt = (lanczos3_taps_bound(height, nheight) + 3) & ~3;
         const int ht = lanczos3_taps_bound(width, nwidth);
-        const int px = rhf <= 0.25f ? 4 * kFpTile : (rhf <= 0.5f ? 2 * kFpTile : kFpTile);
+        int px = rhf <= 0.25f ? 4 * kFpTile : (rhf <= 0.5f ? 2 * kFpTile : kFpTile);
+        int py_max = kFpTile;
+        if (const char *e = getenv("SGX_K3_WIDE_PX")) px = atoi(e);   // tuning: 64 / 128 / 256
+        if (const char *e = getenv("SGX_K3_WIDE_PY")) py_max = atoi(e); // tuning: 64 / 32 / 16
         const int gp = wide_pitch((int)std::ceil((px - 1) * (double)rhf) + ht + 2);
+        // tile height: fewer rows per tile mean more redundant source rows (the Lanczos halo) but more resident
+        // CTAs to hide the load latency of phase A; weights fitted to the C4 sweep on B200
         RenderTiling pick{};
-        for (int py = kFpTile; py >= 16; py >>= 1) {
+        double best = 1e300;
+        for (int py = py_max; py >= 16; py >>= 1) {
             const int rcap = ((int)std::ceil((py - 1) * (double)rvf) + vt + 2 + 7) & ~7;
-            const size_t smem = ((size_t)rcap * gp + (size_t)gp * kFpTP) * sizeof(float);
+            const size_t smem = ((size_t)rcap * gp + (size_t)gp * (py + 4)) * sizeof(float);
             if (smem > (size_t)kWideMaxSmem) continue;
-            if (pick.fast == 0) pick = RenderTiling{px, py, gp, rcap, smem, 1};
-            if (smem <= 113 * 1024) { pick = RenderTiling{px, py, gp, rcap, smem, 1}; break; } // two CTAs per SM
+            const int ctas = std::min(4, (int)((size_t)(227 * 1024) / (smem + 1024)));
+            const double halo = (double)rcap / std::max(1.0, py * (double)rvf);
+            const double occ = ctas >= 4 ? 1.0 : (ctas == 3 ? 1.05 : (ctas == 2 ? 1.25 : 1.6));
+            const double cost = (0.5 + 0.5 * halo) * occ;
+            if (cost < best) { best = cost; pick = RenderTiling{px, py, gp, rcap, smem, 1}; }
         }
         static const bool no_wide = getenv("SGX_K3_NOWIDE") && atoi(getenv("SGX_K3_NOWIDE")) == 1;
         if (pick.fast == 1 && !no_wide) return pick;

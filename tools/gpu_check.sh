@@ -1,15 +1,17 @@
 #!/bin/bash
-# parity tests + benches (c5 headline, c3, c1)
+# parity tests + benches (c5 headline, c3, c2, c1 and the six points of the c4 FFT-size sweep)
 mkdir -p gpurun_out
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 tail -3 gpurun_out/smoke.log
 timeout 1500 python -m pytest tests -m gpu -q -rA -s --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 grep -E "passed|failed|error" gpurun_out/pytest_gpu.log | tail -5
 grep -E "^FAILED" gpurun_out/pytest_gpu.log | head -20
-for wl in c5 c3 c2 c1; do
+for wl in c5 c3 c2 c1 c4_512 c4_1024 c4_2048 c4_4096 c4_8192 c4_16384; do
   extra=""; [ "$wl" != "c5" ] && extra="--no-cpu --no-e2e"
   [ -n "$BENCH_FAST" ] && extra="--no-cpu --no-e2e"
-  timeout 900 python bench.py --workload $wl --steps 5 --warmup 3 $extra > gpurun_out/bench_$wl.log 2> gpurun_out/bench_$wl.err; echo "bench $wl exit $?" >> gpurun_out/bench_$wl.err
+  sel="--workload $wl"
+  case $wl in c4_*) sel="--workload c4 --n-fft ${wl#c4_} --tracks 4";; esac
+  timeout 900 python bench.py $sel --steps 5 --warmup 3 $extra > gpurun_out/bench_$wl.log 2> gpurun_out/bench_$wl.err; echo "bench $wl exit $?" >> gpurun_out/bench_$wl.err
   python - <<PY
 import json
 try:

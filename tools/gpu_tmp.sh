@@ -17,4 +17,12 @@ PY
 B="timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu --no-e2e"
 for F in 512 4096 8192 16384; do
   run c4_${F} X=1 $B --workload c4 --n-fft $F --tracks 4
+  run c4_${F}_py32 SGX_K3_WIDE_PY=32 $B --workload c4 --n-fft $F --tracks 4
+  run c4_${F}_py16 SGX_K3_WIDE_PY=16 $B --workload c4 --n-fft $F --tracks 4
 done
+for F in 4096 8192 16384; do
+  run c4_${F}_px128 SGX_K3_WIDE_PX=128 $B --workload c4 --n-fft $F --tracks 4
+  run c4_${F}_px256 SGX_K3_WIDE_PX=256 $B --workload c4 --n-fft $F --tracks 4
+  run c4_${F}_px512 SGX_K3_WIDE_PX=512 $B --workload c4 --n-fft $F --tracks 4
+done
+run c4_512_px128 SGX_K3_WIDE_PX=128 $B --workload c4 --n-fft 512 --tracks 4
