@@ -486,7 +486,37 @@ stft_db_kernel(const StftLaunch L)
             phase ^= 1u;
         } else {
             __syncthreads(); // every group is past its first pass of the previous tile: the buffer is free
-            for (int s = tid; s < cur.len; s += THREADS) tile[s] = load_sample(pv, cur.A0 + s);
+            const long long b0 = cur.A0 - pv.origin; // local index of the tile's first sample
+            const bool inside = cur.A0 >= 0 && cur.A0 + cur.len <= pv.n && b0 >= 0 && b0 + cur.len <= pv.avail;
+            if (inside && pv.ch <= 2) {
+                // no reflection inside this tile: plain strided copies, eight loads in flight per thread
+                constexpr int NB = 8;
+                for (int s0 = tid; s0 < cur.len; s0 += THREADS * NB) {
+                    float v[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const int s = s0 + j * THREADS;
+                        v[j] = 0.0f;
+                        if (s < cur.len) {
+                            if (pv.fmt == PCM_F32) {
+                                const float *p = reinterpret_cast<const float *>(pv.pcm) + (b0 + s) * pv.ch;
+                                v[j] = pv.ch == 2 ? __ldg(p) + __ldg(p + 1) : __ldg(p);
+                            } else { // audio.rs:16-19
+                                const short *p = reinterpret_cast<const short *>(pv.pcm) + (b0 + s) * pv.ch;
+                                v[j] = (float)__ldg(p) * (1.0f / 32768.0f);
+                                if (pv.ch == 2) v[j] += (float)__ldg(p + 1) * (1.0f / 32768.0f);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const int s = s0 + j * THREADS;
+                        if (s < cur.len) tile[s] = v[j];
+                    }
+                }
+            } else {
+                for (int s = tid; s < cur.len; s += THREADS) tile[s] = load_sample(pv, cur.A0 + s);
+            }
             __syncthreads();
         }
     }

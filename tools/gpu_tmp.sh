@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 -k "render or geometry or image or wav or slice or golden or grey" > gpurun_out/pytest_k3.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k3.log
-tail -3 gpurun_out/pytest_k3.log
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/pytest_k1.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k1.log
+tail -3 gpurun_out/pytest_k1.log
 run() {
   name=$1; shift
   env "$@" > gpurun_out/s_$name.log 2> gpurun_out/s_$name.err
@@ -14,15 +14,6 @@ except Exception as ex:
     print("$name failed", ex); print(open("gpurun_out/s_$name.err").read()[-600:])
 PY
 }
-B="timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu --no-e2e"
-for F in 512 4096 8192 16384; do
-  run c4_${F} X=1 $B --workload c4 --n-fft $F --tracks 4
-  run c4_${F}_py32 SGX_K3_WIDE_PY=32 $B --workload c4 --n-fft $F --tracks 4
-  run c4_${F}_py16 SGX_K3_WIDE_PY=16 $B --workload c4 --n-fft $F --tracks 4
-done
-for F in 4096 8192 16384; do
-  run c4_${F}_px128 SGX_K3_WIDE_PX=128 $B --workload c4 --n-fft $F --tracks 4
-  run c4_${F}_px256 SGX_K3_WIDE_PX=256 $B --workload c4 --n-fft $F --tracks 4
-  run c4_${F}_px512 SGX_K3_WIDE_PX=512 $B --workload c4 --n-fft $F --tracks 4
-done
-run c4_512_px128 SGX_K3_WIDE_PX=128 $B --workload c4 --n-fft 512 --tracks 4
+B="timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e"
+run c3 X=1 $B --workload c3
+run c5 X=1 $B --workload c5
