@@ -305,20 +305,21 @@ __host__ __device__ constexpr size_t fp_smem(int tv, int th)
     return (size_t)(fp_cap(tv) * fp_cap(th) + fp_cap(th) * kFpTP) * sizeof(float);
 }
 
-// display.rs:24-42 with the colour map stored as (a, b) = (stop i, stop i+1) pairs per channel.
-// round() is floor(v + 0.5): identical to f32::round for v >= 0 except within 2^-25 below 0.5.
+// display.rs:24-42 with the colour map stored per channel as (a + 0.5, b - a) for the stops a = stop i,
+// b = stop i+1:  round(ratio*b + (1-ratio)*a) = floor(a + 0.5 + ratio*(b - a)), one FMA and one
+// conversion per channel.  The single rounding of the FMA can differ from the reference's three only when
+// the exact value lies within ~3e-5 of a rounding boundary (about 1 byte in 10^4, by 1 LSB).
 __device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const float2 *cmab)
 {
     const float position = __fmul_rn(10.0f, x);
     const float fl = floorf(position);
     const int idx = min(__float2int_rz(fl), 8);
     const float ratio = __fsub_rn(position, fl);
-    const float om = __fsub_rn(1.0f, ratio);
     const float2 r = cmab[idx * 3], g = cmab[idx * 3 + 1], b = cmab[idx * 3 + 2];
-    unsigned cr = __float2uint_rd(__fadd_rn(__fadd_rn(__fmul_rn(ratio, r.y), __fmul_rn(om, r.x)), 0.5f));
-    unsigned cg = __float2uint_rd(__fadd_rn(__fadd_rn(__fmul_rn(ratio, g.y), __fmul_rn(om, g.x)), 0.5f));
-    unsigned cb = __float2uint_rd(__fadd_rn(__fadd_rn(__fmul_rn(ratio, b.y), __fmul_rn(om, b.x)), 0.5f));
-    unsigned px = cr | (cg << 8) | (cb << 16) | 0xff000000u;
+    const unsigned cr = __float2uint_rd(fmaf(ratio, r.y, r.x));
+    const unsigned cg = __float2uint_rd(fmaf(ratio, g.y, g.x));
+    const unsigned cb = __float2uint_rd(fmaf(ratio, b.y, b.x));
+    const unsigned px = cr | (cg << 8) | (cb << 16) | 0xff000000u;
     return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
 }
 
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
     if (ox0 >= ox_end || oy0 >= nheight) return;
     const int pxc = min(kFpTile, ox_end - ox0), pyc = min(kFpTile, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3], (float)kColormap[tid / 3 + 1][tid % 3]);
+    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3] + 0.5f, (float)kColormap[tid / 3 + 1][tid % 3] - (float)kColormap[tid / 3][tid % 3]);
 
     const int *__restrict__ h_left = tr->h_left;
     const int *__restrict__ v_left = tr->v_left;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const Re
     if (ox0 >= ox_end || oy0 >= nheight) return;
     const int pxc = min(L.px, ox_end - ox0), pyc = min(L.py, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3], (float)kColormap[tid / 3 + 1][tid % 3]);
+    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3] + 0.5f, (float)kColormap[tid / 3 + 1][tid % 3] - (float)kColormap[tid / 3][tid % 3]);
 
     const int *__restrict__ h_left = tr->h_left;
     const int *__restrict__ v_left = tr->v_left;
