@@ -699,24 +699,30 @@ stft_db_kernel(const StftLaunch L)
 #pragma unroll
             for (int p = 0; p < NPR; ++p) {
                 const int ba = (2 * p) * RL, bb = (2 * p + 1) * RL; // register blocks of butterflies bA, bB
-                if (p == 0 && gt == 0) {
-                    // butterfly 0 pairs with itself: Z[r NSL] <-> Z[(RL - r) NSL]; r = 0 and r = RL/2 are self-conjugate
-                    split_pair(0, csA[p][0], re[ba], im[ba], re[ba], im[ba], true);
+                // Thread 0 holds the two self-paired butterflies: 0 (Z[r NSL] <-> Z[(RL - r) NSL], r = 0 and RL/2
+                // self-conjugate) and NSL/2 (Z[NSL/2 + r NSL] <-> Z[NSL/2 + (RL-1-r) NSL]).  It runs the same
+                // calls as everybody else with its partner operands picked from its own registers, so that its
+                // warp does not execute a second copy of the split (the other warps of the group would wait
+                // for it at the next barrier); only the lone bin H/2 is extra.
+                const bool self = p == 0 && gt == 0;
 #pragma unroll
-                    for (int r = 1; r < RL / 2; ++r)
-                        split_pair(r * NSL, csA[p][r], re[ba + r], im[ba + r], re[ba + RL - r], im[ba + RL - r], true);
-                    split_pair(H / 2, make_float2(0.0f, 1.0f), re[ba + RL / 2], im[ba + RL / 2], re[ba + RL / 2], im[ba + RL / 2], false);
-                    // butterfly NSL/2 pairs with itself: Z[NSL/2 + r NSL] <-> Z[NSL/2 + (RL-1-r) NSL]
+                for (int r = 0; r < RL / 2; ++r) {
+                    float pr[V], pi[V];
 #pragma unroll
-                    for (int r = 0; r < RL / 2; ++r)
-                        split_pair(NSL / 2 + r * NSL, csB[p][r], re[bb + r], im[bb + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < RL / 2; ++r) {
-                        split_pair(bA[p] + r * NSL, csA[p][r], re[ba + r], im[ba + r], re[bb + RL - 1 - r], im[bb + RL - 1 - r], true);
-                        split_pair(bB[p] + r * NSL, csB[p][r], re[bb + r], im[bb + r], re[ba + RL - 1 - r], im[ba + RL - 1 - r], true);
+                    for (int v = 0; v < V; ++v) {
+                        pr[v] = re[bb + RL - 1 - r][v]; pi[v] = im[bb + RL - 1 - r][v];
+                        if (p == 0 && self) { pr[v] = re[ba + (r == 0 ? 0 : RL - r)][v]; pi[v] = im[ba + (r == 0 ? 0 : RL - r)][v]; }
                     }
+                    split_pair(bA[p] + r * NSL, csA[p][r], re[ba + r], im[ba + r], pr, pi, true);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        pr[v] = re[ba + RL - 1 - r][v]; pi[v] = im[ba + RL - 1 - r][v];
+                        if (p == 0 && self) { pr[v] = re[bb + RL - 1 - r][v]; pi[v] = im[bb + RL - 1 - r][v]; }
+                    }
+                    split_pair(bB[p] + r * NSL, csB[p][r], re[bb + r], im[bb + r], pr, pi, true);
                 }
+                if (p == 0 && self)
+                    split_pair(H / 2, make_float2(0.0f, 1.0f), re[ba + RL / 2], im[ba + RL / 2], re[ba + RL / 2], im[ba + RL / 2], false);
             }
         } else {
         run_passes<H, PTS, V, G, 1, H>(re, im, sre, sim, gt, grp, L.tw);

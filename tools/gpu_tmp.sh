@@ -17,3 +17,6 @@ PY
 B="timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e"
 run c3 X=1 $B --workload c3
 run c5 X=1 $B --workload c5
+run c4_512 X=1 $B --workload c4 --n-fft 512 --tracks 4
+run c4_1024 X=1 $B --workload c4 --n-fft 1024 --tracks 4
+run c4_4096 X=1 $B --workload c4 --n-fft 4096 --tracks 4
