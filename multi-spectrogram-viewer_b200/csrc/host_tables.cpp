@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace sgx {
@@ -214,6 +215,10 @@ MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int thread
     mb.log2_split = best;
     // block schedule: 32 consecutive work items (filter, lane-of-filter) per block, blocks packed
     // longest-first onto the warps of a thread group
+    // cost of a block in tap iterations (~7 instructions each): its longest lane plus the fixed part --
+    // descriptor fetch, lane reduction, dB and the stores -- which weighs about ten of them
+    int kMelBlockFixed = 10;
+    if (const char *e = getenv("SGX_MEL_FIXED")) kMelBlockFixed = atoi(e);
     const int P = 1 << best, warps = std::max(1, threads_per_group / 32);
     const size_t n_items = n_mel * (size_t)P, n_blocks = (n_items + 31) / 32;
     std::vector<std::pair<int, int>> cost(n_blocks); // (cost, block)
@@ -221,7 +226,7 @@ MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int thread
         int longest = 0;
         for (size_t it = b * 32; it < std::min(n_items, (b + 1) * 32); ++it)
             longest = std::max(longest, (mb.cnt[it / P] + P - 1) / P);
-        cost[b] = {longest + 4, (int)b};
+        cost[b] = {longest + kMelBlockFixed, (int)b};
     }
     std::sort(cost.begin(), cost.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
     std::vector<std::vector<int>> lists(warps);

@@ -1,7 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/pytest_k1.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k1.log
-tail -3 gpurun_out/pytest_k1.log
 run() {
   name=$1; shift
   env "$@" > gpurun_out/s_$name.log 2> gpurun_out/s_$name.err
@@ -15,8 +13,9 @@ except Exception as ex:
 PY
 }
 B="timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e"
-run c3 X=1 $B --workload c3
-run c5 X=1 $B --workload c5
-run c4_512 X=1 $B --workload c4 --n-fft 512 --tracks 4
-run c4_1024 X=1 $B --workload c4 --n-fft 1024 --tracks 4
-run c4_4096 X=1 $B --workload c4 --n-fft 4096 --tracks 4
+for fx in 4 7 10 14 20; do
+run c5_fixed$fx SGX_MEL_FIXED=$fx $B --workload c5
+done
+run c3_fixed4 SGX_MEL_FIXED=4 $B --workload c3
+run c3_fixed10 SGX_MEL_FIXED=10 $B --workload c3
+run c3_fixed20 SGX_MEL_FIXED=20 $B --workload c3
