@@ -721,8 +721,12 @@ stft_db_kernel(const StftLaunch L)
                     }
                     split_pair(bB[p] + r * NSL, csB[p][r], re[bb + r], im[bb + r], pr, pi, true);
                 }
-                if (p == 0 && self)
-                    split_pair(H / 2, make_float2(0.0f, 1.0f), re[ba + RL / 2], im[ba + RL / 2], re[ba + RL / 2], im[ba + RL / 2], false);
+                if (p == 0 && self) { // X[H/2] = conj(Z[H/2])
+                    float ni[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) ni[v] = -im[ba + RL / 2][v];
+                    emit(H / 2, padi(H / 2) * V, re[ba + RL / 2], ni);
+                }
             }
         } else {
         run_passes<H, PTS, V, G, 1, H>(re, im, sre, sim, gt, grp, L.tw);
