@@ -309,18 +309,28 @@ __host__ __device__ constexpr size_t fp_smem(int tv, int th)
 // b = stop i+1:  round(ratio*b + (1-ratio)*a) = floor(a + 0.5 + ratio*(b - a)), one FMA and one
 // conversion per channel.  The single rounding of the FMA can differ from the reference's three only when
 // the exact value lies within ~3e-5 of a rounding boundary (about 1 byte in 10^4, by 1 LSB).
-__device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const float2 *cmab)
+__device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const float4 *cmab)
 {
     const float position = __fmul_rn(10.0f, x);
     const float fl = floorf(position);
     const int idx = min(__float2int_rz(fl), 8);
     const float ratio = __fsub_rn(position, fl);
-    const float2 r = cmab[idx * 3], g = cmab[idx * 3 + 1], b = cmab[idx * 3 + 2];
-    const unsigned cr = __float2uint_rd(fmaf(ratio, r.y, r.x));
-    const unsigned cg = __float2uint_rd(fmaf(ratio, g.y, g.x));
+    const float4 rg = cmab[idx * 2], b = cmab[idx * 2 + 1]; // (r: a+.5, b-a, g: a+.5, b-a), (b: a+.5, b-a, -, -)
+    const unsigned cr = __float2uint_rd(fmaf(ratio, rg.y, rg.x));
+    const unsigned cg = __float2uint_rd(fmaf(ratio, rg.w, rg.z));
     const unsigned cb = __float2uint_rd(fmaf(ratio, b.y, b.x));
     const unsigned px = cr | (cg << 8) | (cb << 16) | 0xff000000u;
     return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
+}
+// segment i of the colour map as two float4: per channel (stop i + 0.5, stop i+1 - stop i)
+__device__ __forceinline__ void fill_colour_table(float4 *cmab, int tid)
+{
+    if (tid < 9) {
+        float a[3], d[3];
+        for (int c = 0; c < 3; ++c) { a[c] = (float)kColormap[tid][c] + 0.5f; d[c] = (float)kColormap[tid + 1][c] - (float)kColormap[tid][c]; }
+        cmab[tid * 2] = make_float4(a[0], d[0], a[1], d[1]);
+        cmab[tid * 2 + 1] = make_float4(a[2], d[2], 0.0f, 0.0f);
+    }
 }
 
 template <int TV, int TH, bool FROM_DB, int CH>
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
 {
     constexpr int RCAP = fp_cap(TV), FCAP = fp_cap(TH), GP = FCAP; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
-    __shared__ float2 cmab[27];
+    __shared__ float4 cmab[18];
     float *G = rsm;
     float *Tm = rsm + RCAP * GP;         // [frame][out row]
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
@@ -339,7 +349,7 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
     if (ox0 >= ox_end || oy0 >= nheight) return;
     const int pxc = min(kFpTile, ox_end - ox0), pyc = min(kFpTile, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3] + 0.5f, (float)kColormap[tid / 3 + 1][tid % 3] - (float)kColormap[tid / 3][tid % 3]);
+    fill_colour_table(cmab, tid);
 
     const int *__restrict__ h_left = tr->h_left;
     const int *__restrict__ v_left = tr->v_left;
@@ -427,8 +437,8 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
                     t2 = fmaf(v.z, wv[i], t2); t3 = fmaf(v.w, wv[i], t3);
                 }
                 float *t_out = Tm + (fq * 4) * kFpTP + oyl;
-                t_out[0] = clamp_pos(t0); t_out[kFpTP] = clamp_pos(t1);
-                t_out[2 * kFpTP] = clamp_pos(t2); t_out[3 * kFpTP] = clamp_pos(t3);
+                t_out[0] = clamp_fin(t0); t_out[kFpTP] = clamp_fin(t1);
+                t_out[2 * kFpTP] = clamp_fin(t2); t_out[3 * kFpTP] = clamp_fin(t3);
             }
         }
     }
@@ -457,7 +467,7 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
 #pragma unroll
                 for (int j = 0; j < 4; ++j, pix += opitch) {
                     if (rq * 4 + j < pyc) {
-                        const unsigned c = grey_to_rgba_fast(clamp_pos(t[j]), cmab);
+                        const unsigned c = grey_to_rgba_fast(clamp_fin(t[j]), cmab);
                         if (CH == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
                         else { outp[pix * 3] = (unsigned char)c; outp[pix * 3 + 1] = (unsigned char)(c >> 8); outp[pix * 3 + 2] = (unsigned char)(c >> 16); }
                     }
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const Re
 {
     const int RCAP = L.rv_max, GP = L.fc; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
-    __shared__ float2 cmab[27];
+    __shared__ float4 cmab[18];
     float *G = rsm;
     float *Tm = rsm + (size_t)RCAP * GP;  // [frame][out row], pitch TP
     const int TP = L.py + 4;              // 68 / 36 / 20: multiples of 4 with an odd quarter
@@ -504,7 +514,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const Re
     if (ox0 >= ox_end || oy0 >= nheight) return;
     const int pxc = min(L.px, ox_end - ox0), pyc = min(L.py, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 27) cmab[tid] = make_float2((float)kColormap[tid / 3][tid % 3] + 0.5f, (float)kColormap[tid / 3 + 1][tid % 3] - (float)kColormap[tid / 3][tid % 3]);
+    fill_colour_table(cmab, tid);
 
     const int *__restrict__ h_left = tr->h_left;
     const int *__restrict__ v_left = tr->v_left;

@@ -400,3 +400,27 @@ def test_extreme_render_geometry(msv, orc, px, nh):
     if got.size:
         assert_pixels_close(got.reshape(imgs[0].shape), imgs[0], f"px={px} nh={nh}", max_mismatch_frac=0.02)
     mt.close()
+
+
+@pytest.mark.parametrize("n_fft,hop,px,nh,seconds", [
+    (512, 128, 100.0, 500, 8),      # C4 short window: 3.4x horizontal minification (21 taps per column)
+    (8192, 2048, 100.0, 500, 20),   # C4 long window: 8x vertical minification, horizontal magnification (256-column tiles)
+    (16384, 4096, 100.0, 500, 30),  # 16x vertical minification (~100 taps per row)
+    (4096, 1024, 1000.0, 33, 6),    # a handful of frames under ~1,300 rows per tile: row-major fill of the grey tile
+])
+def test_wide_render_paths(msv, orc, n_fft, hop, px, nh, seconds):
+    """The wide K3 path (runtime tap counts, source window of a tile in shared memory) through the public
+    MultiTrack call, linear frequency scale as in the C4 sweep, against the oracle's resize."""
+    sr = 44100
+    x = synth.base_clip(seconds * sr, sr, 404 + n_fft)
+    settings = msv.Settings.default(freq_scale=msv.FREQ_LINEAR, win_length=n_fft, hop_length=hop, n_fft=n_fft)
+    imgs, mx, mn = _oracle_batch(orc, msv, [x], [sr], settings, nheight=nh, px=px, channels=4)
+    mt = msv.MultiTrack(settings)
+    mt.add_tracks_pcm([0], [x], [sr])
+    assert_range_close((mt.get_max_db(), mt.get_min_db()), (mx, mn), what=f"n_fft={n_fft}")
+    got = mt.get_spec_image_rgba(0, px, nh).reshape(imgs[0].shape)
+    dmx, frac = assert_pixels_close(got, imgs[0], f"wide render n_fft={n_fft} px={px} nh={nh}")
+    print(f"wide render n_fft={n_fft}: image {got.shape}, max diff {dmx}, mismatching bytes {frac:.2e}")
+    rgb = mt.get_spec_image(0, px, nh).reshape(nh, -1, 3)
+    assert np.array_equal(rgb, got[..., :3])
+    mt.close()

@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 -rA -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+grep -E "passed|failed|pytest exit" gpurun_out/pytest_gpu.log | tail -3
+grep -E "wide render" gpurun_out/pytest_gpu.log | head
 run() {
   name=$1; shift
   env "$@" > gpurun_out/s_$name.log 2> gpurun_out/s_$name.err
@@ -13,9 +16,5 @@ except Exception as ex:
 PY
 }
 B="timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e"
-for fx in 4 7 10 14 20; do
-run c5_fixed$fx SGX_MEL_FIXED=$fx $B --workload c5
-done
-run c3_fixed4 SGX_MEL_FIXED=4 $B --workload c3
-run c3_fixed10 SGX_MEL_FIXED=10 $B --workload c3
-run c3_fixed20 SGX_MEL_FIXED=20 $B --workload c3
+run c5 X=1 $B --workload c5
+run c3 X=1 $B --workload c3
