@@ -373,7 +373,10 @@ template <int LOG2H, int PTS, int V, int G, int MC> struct K1Traits {
     static constexpr int MIN_CTAS = MC; // resident CTAs per SM the register budget is shaped for
 };
 
-template <int LOG2H, int PTS, int V, int G, int MC>
+// MEL: the launch projects onto a mel filterbank (MODE_MEL_DB).  A compile-time flag rather than a test of
+// L.mode: the code of the other output modes (and their branch targets) is then absent from the mel kernel's
+// instruction stream, which is long enough for instruction fetch to show up in the stall profile.
+template <int LOG2H, int PTS, int V, int G, int MC, bool MEL>
 __global__ void __launch_bounds__(K1Traits<LOG2H, PTS, V, G, MC>::THREADS, MC)
 stft_db_kernel(const StftLaunch L)
 {
@@ -398,7 +401,7 @@ stft_db_kernel(const StftLaunch L)
     // under the remaining passes, the split and the mel projection of the current one.
     float *bank = fftbuf + (size_t)G * 2 * PADH * V; // dedicated filterbank region (L.bank_floats floats), if any
     const float *bank_src = nullptr;                  // whose taps it currently holds
-    const int mode = L.mode;
+    const int mode = MEL ? (int)MODE_MEL_DB : L.mode;
     unsigned *done_cnt = reinterpret_cast<unsigned *>(smem_raw + 8); // warps that have consumed the current tile
     if (L.staged) {
         if (tid == 0) { mbar_init(mbar, 1); *done_cnt = 0u; }
@@ -468,7 +471,7 @@ stft_db_kernel(const StftLaunch L)
     (void)T;
 
     // ---- filterbank of this track into its dedicated region (once per CTA and track) ----------------
-    if (mode == MODE_MEL_DB && L.bank_floats > 0 && td->mel_w != bank_src) {
+    if (MEL && L.bank_floats > 0 && td->mel_w != bank_src) {
         __syncthreads(); // other groups may still be projecting frames of the previous track
         const int nnz = __ldg(td->mel_cnt + 1);
         const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo);
@@ -600,7 +603,7 @@ stft_db_kernel(const StftLaunch L)
             float mg[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) mg[v] = sqrt_approx(fmaf(xr[v], xr[v], xi[v] * xi[v])); // lib.rs:124
-            if (mode == MODE_MEL_DB) {
+            if (MEL) {
                 st_vec<V>(sre + spos, mg);
             } else {
 #pragma unroll
@@ -672,7 +675,7 @@ stft_db_kernel(const StftLaunch L)
                     ld_vec<V>(sim + sb + (r * NSL / 8 * 9) * V, im[(2 * p + 1) * RL + r]);
                 }
             }
-            if (mode == MODE_MEL_DB) group_sync<G, NT>(grp); // the buffer now becomes the magnitude array
+            if (MEL) group_sync<G, NT>(grp); // the buffer now becomes the magnitude array
 #pragma unroll
             for (int b = 0; b < 2 * NPR; ++b) {
                 float2 w[RL];
@@ -770,7 +773,7 @@ stft_db_kernel(const StftLaunch L)
         // and the host hands every warp of the group a balanced list of blocks (longest-first packing).
         // The filterbank taps and descriptors are first staged in the imaginary plane of the exchange
         // buffer -- it is dead once the spectrum has been read -- so the tap loop only touches shared memory.
-        if (mode == MODE_MEL_DB) {
+        if (MEL) {
             constexpr int NWARPS = NT / 32;
             const int *__restrict__ sched = td->mel_cnt; // {slots, taps, staged, 0, block ids [slots][NWARPS]}
             const int nslots = __ldg(sched), nnz = __ldg(sched + 1);
@@ -1151,11 +1154,11 @@ int resident_sms()
     return sms > 0 ? sms : 148;
 }
 
-template <int LOG2H, int PTS, int V, int G, int MC>
-cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
+template <int LOG2H, int PTS, int V, int G, int MC, bool MEL>
+cudaError_t launch_one_mode(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
     using TR = K1Traits<LOG2H, PTS, V, G, MC>;
-    auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC>;
+    auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC, MEL>;
     cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     if (e != cudaSuccess) return e;
     // persistent CTAs: as many as are resident at once, each walking tiles blockIdx.x + k gridDim.x
@@ -1163,6 +1166,12 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
     kern<<<grid, TR::THREADS, smem, stream>>>(L);
     count_launch();
     return cudaGetLastError();
+}
+template <int LOG2H, int PTS, int V, int G, int MC>
+cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
+{
+    return L.mode == MODE_MEL_DB ? launch_one_mode<LOG2H, PTS, V, G, MC, true>(L, smem, stream)
+                                 : launch_one_mode<LOG2H, PTS, V, G, MC, false>(L, smem, stream);
 }
 
 } // namespace
@@ -1172,18 +1181,24 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 // h = 1024 (8 tracks x 10 min, K1 ms): (8,4,2) 2.35 | (8,2,2) 3.09 | (8,2,4) 3.39 | (4,4,1) 2.80 | (4,4,2) 2.85 |
 // (16,2,4) 3.16 | (16,2,2) 3.38 -- sharing index math, twiddles and mel taps across V = 4 frames outweighs the
 // higher occupancy of the V = 2 variants and the fewer exchanges of radix 16.
-#define SGX_K1_TABLE(X) \
-    X(8, 8, 4, 8, 2)    \
-    X(9, 8, 4, 4, 2)    \
+#ifdef SGX_K1_ALTERNATES // the other CTA shapes of the design-space measurements (make TUNE=-DSGX_K1_ALTERNATES)
+#define SGX_K1_ALT(X)   \
     X(9, 8, 4, 8, 1)    \
-    X(10, 8, 4, 4, 1)   \
     X(10, 8, 4, 2, 2)   \
     X(10, 8, 2, 2, 3)   \
     X(10, 4, 4, 1, 4)   \
+    X(11, 8, 4, 1, 2)
+#else
+#define SGX_K1_ALT(X)
+#endif
+#define SGX_K1_TABLE(X) \
+    X(8, 8, 4, 8, 2)    \
+    X(9, 8, 4, 4, 2)    \
+    X(10, 8, 4, 4, 1)   \
     X(11, 8, 4, 2, 1)   \
-    X(11, 8, 4, 1, 2)   \
     X(12, 8, 4, 1, 1)   \
-    X(13, 8, 2, 1, 1)
+    X(13, 8, 2, 1, 1)   \
+    SGX_K1_ALT(X)
 
 bool stft_config_for(size_t n_fft, StftConfig *cfg)
 {
