@@ -805,7 +805,7 @@ stft_db_kernel(const StftLaunch L)
                 float acc[V];
 #pragma unroll
                 for (int v = 0; v < V; ++v) acc[v] = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
                 for (int j = 0; j < njmax; ++j) {
                     const bool on = j < nj;
                     float wgt = 0.0f;
