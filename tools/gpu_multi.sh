@@ -1,5 +1,5 @@
 #!/bin/bash
-# 2-GPU run: NCCL path of the bench + a sharded parity check
+# N-GPU run (NGPU, default 2): sharded parity check, NCCL path of the bench, CPU arm (SKIP_REF=1 to skip)
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/multi_gpus.txt
 N=${NGPU:-2}
@@ -7,4 +7,4 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -5 gpurun_out/multi_check.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.log 2> gpurun_out/bench_n$N.err; echo "bench n$N exit $?"
 tail -c 1500 gpurun_out/bench_n$N.log; tail -3 gpurun_out/bench_n$N.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.log 2>&1; echo "ref exit $?"; tail -c 600 gpurun_out/bench_ref_n$N.log
+[ -n "$SKIP_REF" ] || timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.log 2>&1; echo "ref exit $?"; tail -c 600 gpurun_out/bench_ref_n$N.log
