@@ -143,6 +143,8 @@ print("K1W OK")
     (48000, 30, 100.0, dict(win_length=4096, hop_length=256, n_fft=4096, n_mel=128)),  # C3 shape, 16-tap horizontal path
     (16000, 25, 7.5, {}),                                                      # zoomed out: general render path
     (22050, 9, 400.0, dict(freq_scale=0)),                                     # zoomed in, linear scale
+    (44100, 30, 100.0, dict(freq_scale=0, win_length=8192, hop_length=2048, n_fft=8192)),  # C4 long window: wide path, 256-column tiles
+    (44100, 12, 100.0, dict(freq_scale=0, win_length=512, hop_length=128, n_fft=512)),     # C4 short window: wide path, 21 horizontal taps
 ])
 def test_time_sliced_track_equals_whole_track(msv, sr, seconds, px, settings_kw):
     """n3: one track cut into time slices -- each holding only the samples its strip of columns needs --

@@ -1,5 +1,6 @@
 #!/bin/bash
-# K1 per FFT size (C4 points, 4 tracks) under the default and an alternative CTA shape; plus C3
+# K1 per FFT size (C4 points, 4 tracks) under the default and an alternative CTA shape; plus C3.
+# The alternative shapes exist only in a library built with `make TUNE=-DSGX_K1_ALTERNATES`.
 mkdir -p gpurun_out
 run() {
   name=$1; shift
@@ -17,7 +18,6 @@ B="timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu --no-e2e"
 for F in 512 1024 2048 4096 8192 16384; do
   run c4_${F} X=1 $B --workload c4 --n-fft $F --tracks 4
 done
-run c4_512_g16 SGX_K1_VARIANT=8,4,16 $B --workload c4 --n-fft 512 --tracks 4
 run c4_512_g8 SGX_K1_VARIANT=8,4,8 $B --workload c4 --n-fft 512 --tracks 4
 run c4_1024_g8 SGX_K1_VARIANT=8,4,8 $B --workload c4 --n-fft 1024 --tracks 4
 run c4_1024_g4 SGX_K1_VARIANT=8,4,4 $B --workload c4 --n-fft 1024 --tracks 4
