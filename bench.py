@@ -301,7 +301,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         # host thread, half a step out of phase.  Inside ONE step the global dB range forces upload -> analysis ->
         # render -> download in sequence, so a single handle uses one PCIe direction at a time; two handles let the
         # upload of one batch run under the download of the other.  Reported next to the headline, not instead of it.
-        if not args.no_e2e2:
+        if not args.no_e2e2 and world == 1:  # one rank only: it pins a second set of output buffers on the host
             import threading
             mt3 = msv.MultiTrack(st, device=local_rank)
             host_out2 = [torch.empty(img_bytes, dtype=torch.uint8).pin_memory() for _ in range(e2e_tracks)]
