@@ -33,6 +33,8 @@ struct StftTrack {
     const int *mel_lo, *mel_cnt, *mel_off; // mel_lo points at packed int4 {lo, cnt, off, 0} per filter
     const float *mel_w;
     int mel_log2p;
+    const int *melp;       // block-padded copy of the bank (host_tables.h MelBands::packed), or null
+    int melp_nwb, melp_nblk; // its tap words and blocks: 32-bit words in total = nwb + 34 * nblk
     unsigned *range_slot;  // [2] order-preserving encodings of (max, min) dB; may be null
     int tile_begin;        // first CTA tile of this track inside the launch
 };

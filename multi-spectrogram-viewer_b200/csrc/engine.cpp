@@ -121,6 +121,8 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
         tt.mel_w.upload(mb.w.data(), mb.w.size(), s);
         tt.mel_log2p = mb.log2_split;
         tt.mel_nnz = (int)mb.w.size();
+        tt.melp.upload(mb.packed.data(), mb.packed.size(), s);
+        tt.melp_nwb = mb.packed_nwb; tt.melp_nblk = mb.packed_nblk;
     }
     SGX_CUDA(cudaStreamSynchronize(s)); // host vectors die here
 }
@@ -136,6 +138,7 @@ static StftTrack make_desc(const void *d_pcm, int fmt, size_t n, uint32_t ch, si
     d.n_frames = (int)T; d.win_f = tt.win_f.p; d.out = out; d.n_out = (int)n_out;
     d.mel_lo = tt.mel_lo.p; d.mel_cnt = tt.mel_cnt.p; d.mel_off = tt.mel_off.p; d.mel_w = tt.mel_w.p;
     d.mel_log2p = tt.mel_log2p; d.range_slot = slot; d.tile_begin = 0;
+    d.melp = tt.melp_nblk > 0 ? tt.melp.p : nullptr; d.melp_nwb = tt.melp_nwb; d.melp_nblk = tt.melp_nblk;
     return d;
 }
 
@@ -380,7 +383,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         if (set_.freq_scale == SGX_FREQ_MEL)
             for (size_t id : kv.second) {
                 const TrackTables &tt = *tracks_.at(id).tables;
-                bank_floats = std::max(bank_floats, ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel);
+                bank_floats = std::max(bank_floats, cfg.fused ? tt.melp_words() : ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel);
             }
         Group g{kv.first.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats), 0};
         g.tables = tracks_.at(kv.second.front()).tables;
@@ -700,7 +703,7 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     d_in.ensure(n + 16); d_out.ensure(elems);
     SGX_CUDA(cudaMemcpyAsync(d_in.p, input, n * sizeof(float), cudaMemcpyHostToDevice, s));
     StftTrack d = make_desc(d_in.p, PCM_F32, n, 1, win, hop, n_fft, (size_t)T, tt, d_out.p, n_out, nullptr);
-    const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop, mode == MODE_MEL_DB ? ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel : 0);
+    const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop, mode != MODE_MEL_DB ? 0 : (pl.cfg.fused ? tt.melp_words() : ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel));
     DevBuf<StftTrack> &dd = ws.desc; dd.upload(&d, 1, s);
     StftLaunch L{};
     L.tracks = dd.p; L.n_tracks = 1;

@@ -68,6 +68,9 @@ struct TrackTables {
     DevBuf<float> mel_w;
     int mel_log2p = 0;
     int mel_nnz = 0;
+    DevBuf<int> melp;                      // block-padded copy of the bank (MelBands::packed)
+    int melp_nwb = 0, melp_nblk = 0;
+    int melp_words() const { return melp_nwb + 34 * melp_nblk; }
 };
 
 struct AxisTableDev {

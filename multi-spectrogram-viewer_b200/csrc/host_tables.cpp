@@ -243,6 +243,32 @@ MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int thread
     mb.sched[0] = (int)slots; mb.sched[1] = (int)nnz; mb.sched[2] = staged ? 1 : 0; mb.sched[3] = 0;
     for (int w = 0; w < warps; ++w)
         for (size_t i = 0; i < lists[w].size(); ++i) mb.sched[4 + i * warps + w] = lists[w][i];
+    // block-padded, tap-major copy (see MelBands::packed)
+    {
+        std::vector<int> off(n_blocks), nj4(n_blocks);
+        size_t nwb = 0;
+        for (size_t b = 0; b < n_blocks; ++b) {
+            int longest = 0;
+            for (size_t it = b * 32; it < std::min(n_items, (b + 1) * 32); ++it) {
+                const int pl = (int)(it % P), c = mb.cnt[it / P];
+                longest = std::max(longest, c > pl ? (c - pl + P - 1) / P : 0);
+            }
+            off[b] = (int)nwb; nj4[b] = std::max(4, (longest + 3) & ~3);
+            nwb += (size_t)32 * nj4[b];
+        }
+        mb.packed.assign(nwb + 32 * n_blocks + 2 * n_blocks, 0);
+        float *wb = reinterpret_cast<float *>(mb.packed.data());
+        int *lo_item = mb.packed.data() + nwb;
+        int *desc = lo_item + 32 * n_blocks;
+        for (size_t it = 0; it < n_items; ++it) {
+            const size_t b = it / 32, lane = it % 32, m = it / P;
+            const int pl = (int)(it % P), c = mb.cnt[m];
+            lo_item[it] = mb.lo[m] + pl;
+            for (int j = 0; pl + j * P < c; ++j) wb[off[b] + 32 * j + lane] = mb.w[mb.off[m] + pl + j * P];
+        }
+        for (size_t b = 0; b < n_blocks; ++b) { desc[2 * b] = off[b]; desc[2 * b + 1] = nj4[b]; }
+        mb.packed_nwb = (int)nwb; mb.packed_nblk = (int)n_blocks;
+    }
     return mb;
 }
 

@@ -41,6 +41,12 @@ struct MelBands {
     int max_cnt = 0;
     int log2_split = 0;            // lanes cooperating on one filter (power of two <= 32)
     std::vector<int> sched;        // {slots, taps, staged, 0, block ids [slots][warps]}: balanced block lists per warp
+    // Block-padded copy of the bank for the kernels whose last FFT pass is fused with the split (they keep the
+    // magnitudes unpadded).  32-bit words: taps [sum_b 32 * nj4_b] (block b, tap j of work item i at
+    // off_b + 32 j + i, zero beyond an item's own taps; nj4_b = longest item of the block rounded up to 4),
+    // first bin per work item [32 * n_blocks], then {off_b, nj4_b} per block.  Work item = filter * P + lane-of-filter.
+    std::vector<int> packed;
+    int packed_nwb = 0, packed_nblk = 0;
 };
 MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group,
                         size_t stage_capacity_floats);

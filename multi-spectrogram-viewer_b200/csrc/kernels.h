@@ -20,6 +20,7 @@ struct StftConfig {
     size_t fft_smem;       // bytes of FFT exchange buffers
     bool generic;          // small-F fallback kernel (one CTA per frame)
     bool warp_per_frame;   // n_fft = 2048: K1W, one warp per frame (persistent CTAs)
+    bool fused;            // last FFT pass fused with the split: magnitudes unpadded, block-padded mel bank
 };
 bool stft_config_for(size_t n_fft, StftConfig *cfg);
 size_t stft_max_dynamic_smem();

@@ -65,6 +65,15 @@ __device__ __forceinline__ float sqrt_approx(float x)
     return y;
 }
 
+// lg2.approx.ftz.f32: one MUFU, absolute error <= 2^-22 (PTX ISA); callers pass normal numbers only, so the
+// subnormal pre-scaling that __log2f wraps around it is dead weight
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS) ----------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p)
 {
@@ -403,10 +412,11 @@ stft_db_kernel(const StftLaunch L)
     const float *bank_src = nullptr;                  // whose taps it currently holds
     const int mode = MEL ? (int)MODE_MEL_DB : L.mode;
     unsigned *done_cnt = reinterpret_cast<unsigned *>(smem_raw + 8); // warps that have consumed the current tile
-    if (L.staged) {
-        if (tid == 0) { mbar_init(mbar, 1); *done_cnt = 0u; }
-        __syncthreads();
-    }
+    // the exchange planes start out finite: the block-padded mel path multiplies whatever lies just beyond a
+    // filter's last bin (padding holes, the slack above bin H) by zero weights
+    for (int i = gt; i < 2 * PADH * V; i += NT) sre[i] = 0.0f;
+    if (L.staged && tid == 0) { mbar_init(mbar, 1); *done_cnt = 0u; }
+    __syncthreads();
     unsigned phase = 0;
     // The descriptor of the track the CTA is working on is kept in shared memory: finding a tile's place
     // then costs a few shared loads instead of a chain of dependent global ones at every tile.
@@ -471,13 +481,26 @@ stft_db_kernel(const StftLaunch L)
     (void)T;
 
     // ---- filterbank of this track into its dedicated region (once per CTA and track) ----------------
-    if (MEL && L.bank_floats > 0 && td->mel_w != bank_src) {
+    // melp: the block-padded copy is used (fused kernels, magnitudes unpadded); else the banded copy, in the
+    // region when it fits, staged per round in the imaginary plane or read through L1 otherwise
+    constexpr int RL_K = last_radix(H, PTS);
+    constexpr bool FUSED_K = (PTS / RL_K) >= 2;
+    const bool melp = MEL && FUSED_K && td->melp != nullptr && td->melp_nwb + 34 * td->melp_nblk <= L.bank_floats;
+    const bool bank_fits = MEL && (melp || ((__ldg(td->mel_cnt + 1) + 3) & ~3) + 4 * n_out <= L.bank_floats);
+    if (MEL && bank_fits && td->mel_w != bank_src) {
         __syncthreads(); // other groups may still be projecting frames of the previous track
-        const int nnz = __ldg(td->mel_cnt + 1);
-        const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo);
-        int4 *msm = reinterpret_cast<int4 *>(bank + ((nnz + 3) & ~3));
-        for (int i = tid; i < nnz; i += THREADS) bank[i] = __ldg(td->mel_w + i);
-        for (int i = tid; i < n_out; i += THREADS) msm[i] = __ldg(meta + i);
+        if (melp) {
+            const int words = td->melp_nwb + 34 * td->melp_nblk;
+            const int *__restrict__ srcw = td->melp;
+            int *dstw = reinterpret_cast<int *>(bank);
+            for (int i = tid; i < words; i += THREADS) dstw[i] = __ldg(srcw + i);
+        } else {
+            const int nnz = __ldg(td->mel_cnt + 1);
+            const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo);
+            int4 *msm = reinterpret_cast<int4 *>(bank + ((nnz + 3) & ~3));
+            for (int i = tid; i < nnz; i += THREADS) bank[i] = __ldg(td->mel_w + i);
+            for (int i = tid; i < n_out; i += THREADS) msm[i] = __ldg(meta + i);
+        }
         __syncthreads();
         bank_src = td->mel_w;
     }
@@ -604,7 +627,7 @@ stft_db_kernel(const StftLaunch L)
 #pragma unroll
             for (int v = 0; v < V; ++v) mg[v] = sqrt_approx(fmaf(xr[v], xr[v], xi[v] * xi[v])); // lib.rs:124
             if (MEL) {
-                st_vec<V>(sre + spos, mg);
+                st_vec<V>(sre + (melp ? idx * V : spos), mg); // block-padded bank: magnitudes at their bin index
             } else {
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
@@ -773,15 +796,67 @@ stft_db_kernel(const StftLaunch L)
         // and the host hands every warp of the group a balanced list of blocks (longest-first packing).
         // The filterbank taps and descriptors are first staged in the imaginary plane of the exchange
         // buffer -- it is dead once the spectrum has been read -- so the tap loop only touches shared memory.
-        if (MEL) {
+        if (MEL && melp) {
+            // Block-padded bank: work item i of block b reads taps wb[off_b + 32 j + lane] (zeros beyond its own)
+            // and the unpadded magnitudes of bins bin0 + j P -- no predicates, no index arithmetic beyond one
+            // add per tap; nj4_b taps for the whole block.
+            constexpr int NWARPS = NT / 32;
+            const int *__restrict__ sched = td->mel_cnt;
+            const int nslots = __ldg(sched);
+            const int lg = td->mel_log2p, P = 1 << lg;
+            const int nwb = td->melp_nwb, nblk = td->melp_nblk;
+            const float *wb = bank;
+            const int *lo_s = reinterpret_cast<const int *>(bank) + nwb;
+            const int2 *desc_s = reinterpret_cast<const int2 *>(lo_s + 32 * nblk);
+            group_sync<G, NT>(grp); // magnitudes of all bins are in the buffer
+            const int wg = gt >> 5, lane = gt & 31;
+            const int stride = V << lg;
+            for (int slot = 0; slot < nslots; ++slot) {
+                const int blk = __ldg(sched + 4 + slot * NWARPS + wg); // warp-uniform
+                if (blk < 0) continue;
+                const int2 bd = desc_s[blk];
+                const int wi = blk * 32 + lane;
+                const int m = wi >> lg, pl = wi & (P - 1);
+                const float *wp = wb + bd.x + lane;
+                const float *mp = sre + lo_s[wi] * V;
+                float acc[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+                for (int j4 = 0; j4 < bd.y; j4 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float wgt = wp[(j4 + u) * 32];
+                        float mg[V];
+                        ld_vec<V>(mp, mg);
+                        mp += stride;
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[v] = fmaf(mg[v], wgt, acc[v]);
+                    }
+                }
+                for (int sh = P >> 1; sh > 0; sh >>= 1)
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], sh);
+                if (m < n_out && pl == 0) {
+                    // Frames beyond the tile's last one were computed from a copy of that last frame (the clamp in
+                    // the first pass), so their dB values may enter the extrema; only the store is predicated.
+                    float *op = out + (size_t)(t0 + fl0) * n_out + m;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const float y = acc[v] > 1e-18f ? 6.02059991327962390f * lg2_approx(acc[v]) : -360.0f; // decibel.rs:33-88
+                        vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+                        if (fl0 + v < nfr) op[(size_t)v * n_out] = y;
+                    }
+                }
+            }
+        } else if (MEL) {
             constexpr int NWARPS = NT / 32;
             const int *__restrict__ sched = td->mel_cnt; // {slots, taps, staged, 0, block ids [slots][NWARPS]}
             const int nslots = __ldg(sched), nnz = __ldg(sched + 1);
-            const bool staged = L.bank_floats > 0 || __ldg(sched + 2) != 0;
+            const bool staged = bank_fits || __ldg(sched + 2) != 0;
             const int lg = td->mel_log2p, P = 1 << lg;
             const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(td->mel_lo); // {lo, cnt, off, 0}
             const float *__restrict__ mw = td->mel_w;
-            const bool dedicated = L.bank_floats > 0; // taps already sit in the CTA's filterbank region
+            const bool dedicated = bank_fits; // taps already sit in the CTA's filterbank region
             float *wsm = dedicated ? bank : sim;
             int4 *msm = reinterpret_cast<int4 *>(wsm + ((nnz + 3) & ~3));
             if (staged && !dedicated) {
@@ -1204,7 +1279,7 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
 {
     if (n_fft < 2 || (n_fft & (n_fft - 1)) != 0 || n_fft > 16384) return false;
     const int h = (int)(n_fft / 2);
-    cfg->n_fft = (int)n_fft; cfg->h = h; cfg->generic = true;
+    cfg->n_fft = (int)n_fft; cfg->h = h; cfg->generic = true; cfg->fused = false;
     cfg->pts = 2; cfg->vec = 1; cfg->groups = 1; cfg->threads = 128; cfg->min_ctas = 1;
     cfg->fft_smem = (size_t)(2 * h) * sizeof(float2) + (size_t)(h + 1) * sizeof(float);
     int want_pts = 0, want_v = 0, want_g = 0;
@@ -1218,6 +1293,7 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
             if (cfg->generic || match) {                                                         \
                 cfg->generic = false; cfg->pts = PTS; cfg->vec = V; cfg->groups = G;             \
                 cfg->threads = TR::THREADS; cfg->fft_smem = TR::FFT_SMEM; cfg->min_ctas = TR::MIN_CTAS; \
+                cfg->fused = (PTS / last_radix(1 << LG, PTS)) >= 2;                                  \
             }                                                                                    \
             chosen = chosen || match;                                                            \
         }                                                                                        \
@@ -1230,7 +1306,7 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
     static const bool k1w_on = getenv("SGX_K1W") && atoi(getenv("SGX_K1W")) == 1;
     cfg->warp_per_frame = false;
     if (h == kWH && k1w_on && want_pts == 0) {
-        cfg->warp_per_frame = true; cfg->generic = false;
+        cfg->warp_per_frame = true; cfg->generic = false; cfg->fused = false;
         cfg->pts = 32; cfg->vec = 1; cfg->groups = kWWarps; cfg->threads = kWThreads; cfg->min_ctas = 1;
         cfg->fft_smem = 0;
     }
