@@ -80,7 +80,10 @@ __host__ __device__ inline float dec_ordered(unsigned e)
 // lg2.approx has an absolute error <= 2^-22 so the dB value is within ~2e-6 dB of libm.
 __device__ __forceinline__ float amp_to_db_dev(float x)
 {
-    return x > 1e-18f ? 6.02059991327962390f * __log2f(x) : -360.0f;
+    // x > 1e-18 is a normal number: the bare MUFU, without __log2f's subnormal pre-scaling (same result)
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    return x > 1e-18f ? 6.02059991327962390f * l : -360.0f;
 }
 
 // One track of a K3 launch.

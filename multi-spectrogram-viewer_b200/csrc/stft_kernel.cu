@@ -629,16 +629,16 @@ stft_db_kernel(const StftLaunch L)
             if (MEL) {
                 st_vec<V>(sre + (melp ? idx * V : spos), mg); // block-padded bank: magnitudes at their bin index
             } else {
+                // frames beyond the tile's last one are copies of it (first-pass clamp): harmless in the extrema
+                float *op = out + (size_t)(t0 + fl0) * (H + 1) + idx;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    if (fl0 + v < nfr) {
-                        float y = mg[v];
-                        if (mode == MODE_LIN_DB) {
-                            y = amp_to_db_dev(y);
-                            vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
-                        }
-                        out[(size_t)(t0 + fl0 + v) * (H + 1) + idx] = y;
+                    float y = mg[v];
+                    if (mode == MODE_LIN_DB) {
+                        y = amp_to_db_dev(y);
+                        vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
                     }
+                    if (fl0 + v < nfr) op[(size_t)v * (H + 1)] = y;
                 }
             }
         };
