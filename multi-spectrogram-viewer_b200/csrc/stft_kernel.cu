@@ -65,15 +65,6 @@ __device__ __forceinline__ float sqrt_approx(float x)
     return y;
 }
 
-// lg2.approx.ftz.f32: one MUFU, absolute error <= 2^-22 (PTX ISA); callers pass normal numbers only, so the
-// subnormal pre-scaling that __log2f wraps around it is dead weight
-__device__ __forceinline__ float lg2_approx(float x)
-{
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 // ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS) ----------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p)
 {
@@ -842,7 +833,7 @@ stft_db_kernel(const StftLaunch L)
                     float *op = out + (size_t)(t0 + fl0) * n_out + m;
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
-                        const float y = acc[v] > 1e-18f ? 6.02059991327962390f * lg2_approx(acc[v]) : -360.0f; // decibel.rs:33-88
+                        const float y = amp_to_db_dev(acc[v]); // decibel.rs:33-88
                         vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
                         if (fl0 + v < nfr) op[(size_t)v * n_out] = y;
                     }
@@ -894,13 +885,13 @@ stft_db_kernel(const StftLaunch L)
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], s);
                 if (valid && pl == 0) {
+                    float *op = out + (size_t)(t0 + fl0) * n_out + m;
 #pragma unroll
-                    for (int v = 0; v < V; ++v)
-                        if (fl0 + v < nfr) {
-                            const float y = amp_to_db_dev(acc[v]);
-                            vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
-                            out[(size_t)(t0 + fl0 + v) * n_out + m] = y;
-                        }
+                    for (int v = 0; v < V; ++v) { // frames beyond the tile's last one are copies of it
+                        const float y = amp_to_db_dev(acc[v]);
+                        vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+                        if (fl0 + v < nfr) op[(size_t)v * n_out] = y;
+                    }
                 }
             };
             for (int slot = 0; slot < nslots; ++slot) {
