@@ -245,13 +245,47 @@ MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int thread
         for (size_t i = 0; i < lists[w].size(); ++i) mb.sched[4 + i * warps + w] = lists[w][i];
     // block-padded, tap-major copy (see MelBands::packed)
     {
+        // Lane order and window shifts inside a block.  At every tap the 8 lanes of a 128-bit shared-memory phase
+        // read the slots (first bin + tap) of their filters; they collide when those are equal mod 8 -- which
+        // neighbouring mel filters are whenever their spacing is even (4-way at 12 bins, 8-way at 8).  All items of
+        // a block run the same number of taps, so (1) the filters (units of P adjacent lanes) may sit in any order
+        // and (2) a filter's window may start q P bins early, its first q taps being zeros: each phase is filled
+        // greedily with the (unit, shift) whose residues are still free.
+        const int unit_lanes = std::min(P, 32), units_per_block = 32 / unit_lanes;
+        const int units_per_phase = std::max(1, 8 / unit_lanes);
+        int max_shift = 2; // 3 and more cut the conflicts further but the longer bank no longer fits next to a 32-frame tile
+        if (const char *e = getenv("SGX_MEL_SHIFT")) max_shift = atoi(e);
+        struct Place { int m, q; };
+        std::vector<std::vector<Place>> placed(n_blocks);
         std::vector<int> off(n_blocks), nj4(n_blocks);
         size_t nwb = 0;
         for (size_t b = 0; b < n_blocks; ++b) {
+            std::vector<int> pending; // filters of this block
+            for (int u = 0; u < units_per_block; ++u) {
+                const size_t m = (b * 32) / P + u;
+                if (m < n_mel) pending.push_back((int)m);
+            }
+            auto residues = [&](int m, int q) {
+                unsigned r = 0;
+                for (int pl = 0; pl < std::min(unit_lanes, 8); ++pl) r |= 1u << ((mb.lo[m] + pl - q * P) & 7);
+                return r;
+            };
             int longest = 0;
-            for (size_t it = b * 32; it < std::min(n_items, (b + 1) * 32); ++it) {
-                const int pl = (int)(it % P), c = mb.cnt[it / P];
-                longest = std::max(longest, c > pl ? (c - pl + P - 1) / P : 0);
+            while (!pending.empty()) {
+                unsigned occ = 0; // residues mod 8 taken in the phase being filled
+                for (int k = 0; k < units_per_phase && !pending.empty(); ++k) {
+                    size_t best_i = 0; int best_q = 0, best_cost = 1 << 30;
+                    for (size_t i = 0; i < pending.size(); ++i)
+                        for (int q = 0; q <= max_shift && q * P <= mb.lo[pending[i]]; ++q) {
+                            const int cost = __builtin_popcount(residues(pending[i], q) & occ) * 16 + q;
+                            if (cost < best_cost) { best_cost = cost; best_i = i; best_q = q; }
+                        }
+                    const int m = pending[best_i];
+                    occ |= residues(m, best_q);
+                    placed[b].push_back(Place{m, best_q});
+                    longest = std::max(longest, (mb.cnt[m] + P - 1) / P + best_q);
+                    pending.erase(pending.begin() + (long)best_i);
+                }
             }
             off[b] = (int)nwb; nj4[b] = std::max(4, (longest + 3) & ~3);
             nwb += (size_t)32 * nj4[b];
@@ -260,13 +294,18 @@ MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int thread
         float *wb = reinterpret_cast<float *>(mb.packed.data());
         int *lo_item = mb.packed.data() + nwb;
         int *desc = lo_item + 32 * n_blocks;
-        for (size_t it = 0; it < n_items; ++it) {
-            const size_t b = it / 32, lane = it % 32, m = it / P;
-            const int pl = (int)(it % P), c = mb.cnt[m];
-            lo_item[it] = mb.lo[m] + pl;
-            for (int j = 0; pl + j * P < c; ++j) wb[off[b] + 32 * j + lane] = mb.w[mb.off[m] + pl + j * P];
+        for (size_t b = 0; b < n_blocks; ++b) {
+            for (int lane = 0; lane < 32; ++lane) lo_item[b * 32 + lane] = (int)(0xffffu << 16); // no filter: nothing is stored
+            for (size_t u = 0; u < placed[b].size(); ++u) {
+                const int m = placed[b][u].m, q = placed[b][u].q, c = mb.cnt[m];
+                for (int pl = 0; pl < unit_lanes; ++pl) {
+                    const size_t lane = u * unit_lanes + pl;
+                    lo_item[b * 32 + lane] = (mb.lo[m] + pl - q * P) | (m << 16);
+                    for (int j = 0; pl + j * P < c; ++j) wb[off[b] + 32 * (j + q) + lane] = mb.w[mb.off[m] + pl + j * P];
+                }
+            }
+            desc[2 * b] = off[b]; desc[2 * b + 1] = nj4[b];
         }
-        for (size_t b = 0; b < n_blocks; ++b) { desc[2 * b] = off[b]; desc[2 * b + 1] = nj4[b]; }
         mb.packed_nwb = (int)nwb; mb.packed_nblk = (int)n_blocks;
     }
     return mb;

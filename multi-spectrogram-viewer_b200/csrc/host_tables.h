@@ -44,7 +44,9 @@ struct MelBands {
     // Block-padded copy of the bank for the kernels whose last FFT pass is fused with the split (they keep the
     // magnitudes unpadded).  32-bit words: taps [sum_b 32 * nj4_b] (block b, tap j of work item i at
     // off_b + 32 j + i, zero beyond an item's own taps; nj4_b = longest item of the block rounded up to 4),
-    // first bin per work item [32 * n_blocks], then {off_b, nj4_b} per block.  Work item = filter * P + lane-of-filter.
+    // {first bin | filter << 16} per lane [32 * n_blocks] (0xffff: no filter), then {off_b, nj4_b} per block.  The P lanes
+    // of a filter are adjacent; the filters of a block are ordered so that the lanes of a shared-memory phase hit
+    // different bank groups.
     std::vector<int> packed;
     int packed_nwb = 0, packed_nblk = 0;
 };

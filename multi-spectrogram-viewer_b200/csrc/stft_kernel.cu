@@ -806,10 +806,10 @@ stft_db_kernel(const StftLaunch L)
                 const int blk = __ldg(sched + 4 + slot * NWARPS + wg); // warp-uniform
                 if (blk < 0) continue;
                 const int2 bd = desc_s[blk];
-                const int wi = blk * 32 + lane;
-                const int m = wi >> lg, pl = wi & (P - 1);
+                const int li = lo_s[blk * 32 + lane];   // first bin | filter << 16
+                const int m = (int)((unsigned)li >> 16), pl = lane & (P - 1);
                 const float *wp = wb + bd.x + lane;
-                const float *mp = sre + lo_s[wi] * V;
+                const float *mp = sre + (li & 0xffff) * V;
                 float acc[V];
 #pragma unroll
                 for (int v = 0; v < V; ++v) acc[v] = 0.0f;
