@@ -10,6 +10,7 @@
 // tiles; HBM sees one read of dB and one write of pixels.
 #include <cstdint>
 #include <cmath>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <type_traits>
 
@@ -309,27 +310,35 @@ __host__ __device__ constexpr size_t fp_smem(int tv, int th)
 // b = stop i+1:  round(ratio*b + (1-ratio)*a) = floor(a + 0.5 + ratio*(b - a)), one FMA and one
 // conversion per channel.  The single rounding of the FMA can differ from the reference's three only when
 // the exact value lies within ~3e-5 of a rounding boundary (about 1 byte in 10^4, by 1 LSB).
-__device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const float4 *cmab)
+// A segment is ONE 16-byte shared load: its six numbers are stored as fp16 pairs -- stops are integers
+// <= 255 and a + 0.5 has 9 significant bits, so fp16 holds them exactly.  (The render kernels are bound
+// by the shared-memory / L1 data pipe; two 128-bit loads per pixel were a third of their wavefronts.)
+__device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const uint4 *cmab)
 {
     const float position = __fmul_rn(10.0f, x);
     const float fl = floorf(position);
     const int idx = min(__float2int_rz(fl), 8);
     const float ratio = __fsub_rn(position, fl);
-    const float4 rg = cmab[idx * 2], b = cmab[idx * 2 + 1]; // (r: a+.5, b-a, g: a+.5, b-a), (b: a+.5, b-a, -, -)
-    const unsigned cr = __float2uint_rd(fmaf(ratio, rg.y, rg.x));
-    const unsigned cg = __float2uint_rd(fmaf(ratio, rg.w, rg.z));
+    const uint4 q = cmab[idx];
+    const float2 r = __half22float2(*reinterpret_cast<const __half2 *>(&q.x));
+    const float2 g = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&q.z));
+    const unsigned cr = __float2uint_rd(fmaf(ratio, r.y, r.x));
+    const unsigned cg = __float2uint_rd(fmaf(ratio, g.y, g.x));
     const unsigned cb = __float2uint_rd(fmaf(ratio, b.y, b.x));
     const unsigned px = cr | (cg << 8) | (cb << 16) | 0xff000000u;
     return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
 }
-// segment i of the colour map as two float4: per channel (stop i + 0.5, stop i+1 - stop i)
-__device__ __forceinline__ void fill_colour_table(float4 *cmab, int tid)
+// segment i of the colour map: per channel half2(stop i + 0.5, stop i+1 - stop i)
+__device__ __forceinline__ void fill_colour_table(uint4 *cmab, int tid)
 {
     if (tid < 9) {
-        float a[3], d[3];
-        for (int c = 0; c < 3; ++c) { a[c] = (float)kColormap[tid][c] + 0.5f; d[c] = (float)kColormap[tid + 1][c] - (float)kColormap[tid][c]; }
-        cmab[tid * 2] = make_float4(a[0], d[0], a[1], d[1]);
-        cmab[tid * 2 + 1] = make_float4(a[2], d[2], 0.0f, 0.0f);
+        unsigned w[3];
+        for (int c = 0; c < 3; ++c) {
+            const __half2 h = __floats2half2_rn((float)kColormap[tid][c] + 0.5f, (float)kColormap[tid + 1][c] - (float)kColormap[tid][c]);
+            w[c] = *reinterpret_cast<const unsigned *>(&h);
+        }
+        cmab[tid] = make_uint4(w[0], w[1], w[2], 0u);
     }
 }
 
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
 {
     constexpr int RCAP = fp_cap(TV), FCAP = fp_cap(TH), GP = FCAP; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
-    __shared__ float4 cmab[18];
+    __shared__ uint4 cmab[9];
     float *G = rsm;
     float *Tm = rsm + RCAP * GP;         // [frame][out row]
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
@@ -502,7 +511,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const Re
 {
     const int RCAP = L.rv_max, GP = L.fc; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
-    __shared__ float4 cmab[18];
+    __shared__ uint4 cmab[9];
     float *G = rsm;
     float *Tm = rsm + (size_t)RCAP * GP;  // [frame][out row], pitch TP
     const int TP = L.py + 4;              // 68 / 36 / 20: multiples of 4 with an odd quarter
