@@ -424,3 +424,31 @@ def test_wide_render_paths(msv, orc, n_fft, hop, px, nh, seconds):
     rgb = mt.get_spec_image(0, px, nh).reshape(nh, -1, 3)
     assert np.array_equal(rgb, got[..., :3])
     mt.close()
+
+
+@pytest.mark.parametrize("kind,n_fft,n_mel", [("dense", 2048, 6), ("dense", 2048, 64), ("dense", 4096, 10), ("ragged", 2048, 96),
+                                              ("ragged", 512, 40), ("ragged", 1024, 33), ("ragged", 16384, 50)])
+def test_arbitrary_filterbank_parity(msv, orc, kind, n_fft, n_mel):
+    """calc_spec takes ANY [bins x n_mel] matrix (lib.rs:131 is a dense dot): dense banks (every filter spans all
+    bins: 32 lanes per filter; the large one does not fit the shared-memory region and takes the banded path) and
+    ragged banks (unordered, overlapping, empty and single-bin filters) through the block-padded mel path."""
+    sr = 44100
+    rng = np.random.default_rng(n_fft + n_mel)
+    bins = n_fft // 2 + 1
+    if kind == "dense":
+        fb = (rng.random((bins, n_mel)) * 2e-3 + 1e-5).astype(np.float32)
+    else:
+        fb = np.zeros((bins, n_mel), dtype=np.float32)
+        for m in range(n_mel):
+            if m % 11 == 5:
+                continue                                   # an empty filter
+            lo = int(rng.integers(0, bins))
+            cnt = 1 if m % 7 == 3 else int(rng.integers(1, max(2, bins // 6)))
+            hi = min(bins, lo + cnt)
+            fb[lo:hi, m] = (rng.random(hi - lo) * 1e-2 + 1e-4).astype(np.float32)
+    x = synth.base_clip(max(5 * n_fft, sr), sr, seed=n_fft * 3 + n_mel)
+    ref = orc.calc_spec(x, n_fft, n_fft // 4, n_fft, None, fb)
+    got = msv.melspectrogram_db(x, n_fft, n_fft // 4, n_fft, None, fb)
+    e, m_ = assert_db_close(got, ref, f"{kind} bank n_fft={n_fft} n_mel={n_mel}")
+    print(f"{kind} bank n_fft={n_fft} n_mel={n_mel}: {e:.2e} dB / {m_:.2e} mag")
+    assert np.array_equal(got <= -359.0, ref <= -359.0)
