@@ -492,6 +492,7 @@ def main():
     ap.add_argument("--n-fft", type=int, default=2048, help="FFT size of the c4 sweep point (512 ... 16384)")
     ap.add_argument("--tracks", type=int, default=0, help="override tracks per GPU (profiling runs only)")
     ap.add_argument("--seconds", type=float, default=0, help="override track length (profiling runs only)")
+    ap.add_argument("--channels", type=int, default=0, help="override the channel count of the workload (experiments only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e2", action="store_true", help="skip the two-batches-in-flight variant of the e2e measurement")
     ap.add_argument("--no-cpu", action="store_true")
@@ -500,6 +501,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = workload(args.workload, args.n_fft)
+    if args.channels:
+        wl["channels"] = args.channels
+        wl["desc"] += f" [channels overridden: {args.channels}]"
     if args.tracks:
         wl["tracks"] = args.tracks; wl["desc"] += f" [OVERRIDE tracks={args.tracks}: not a headline run]"
     if args.seconds:

@@ -48,6 +48,7 @@ struct StftLaunch {
     int staged;            // 1: PCM tile staged in shared memory, 0: direct global loads
     int tile_floats;       // capacity of the staged tile
     int bank_floats;       // > 0: the CTA keeps the track's mel taps + descriptors in a region of its own
+    int stereo_raw;        // 1: the launch holds f32 stereo tracks and its tiles have room for raw interleaved pairs
     const float2 *tw;      // [h]      exp(-2 pi i j / h)
     const float2 *split;   // [h/2+1]  (cos, sin)(k pi / h)                realfft.rs:88-93
     // warp-per-frame kernel (n_fft = 2048)

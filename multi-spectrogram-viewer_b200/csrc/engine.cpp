@@ -385,7 +385,12 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
                 const TrackTables &tt = *tracks_.at(id).tables;
                 bank_floats = std::max(bank_floats, cfg.fused ? tt.melp_words() : ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel);
             }
-        Group g{kv.first.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats), 0};
+        int sample_floats = 1; // f32 stereo tracks stage raw interleaved pairs: twice the room per sample
+        for (size_t id : kv.second) {
+            const Track &t = tracks_.at(id);
+            if (set_.freq_scale == SGX_FREQ_MEL && t.ch == 2 && t.fmt == PCM_F32) sample_floats = 2;
+        }
+        Group g{kv.first.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats, sample_floats), 0};
         g.tables = tracks_.at(kv.second.front()).tables;
         // a track id may appear twice in id_list; the last one wins, launch it once
         std::vector<size_t> uniq;
@@ -413,6 +418,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
         L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
         L.tile_floats = g.tiling.tile_floats; L.bank_floats = g.tiling.bank_floats; L.tw = pl.tw.p; L.split = pl.split.p;
+        L.stereo_raw = g.tiling.sample_floats == 2 ? 1 : 0;
         L.tw2 = pl.tw2.p; L.split_full = pl.split_full.p;
         L.mel_nnz = g.tables ? g.tables->mel_nnz : 0; L.mel_rows = g.tables ? (int)g.tables->n_mel : 0;
         if (!pipelined) { SGX_CUDA(launch_stft(pl.cfg, L, stream_)); continue; }

@@ -31,8 +31,9 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &launch, cudaStr
 // Chooses frames per tile / staging for a set of (hop) values sharing one FFT size.
 // `bank_floats`: shared-memory floats the largest mel filterbank of the launch needs (taps rounded up to 4, plus
 // 4 per filter for its descriptor), 0 when not a mel launch; the planner reports whether it got its own region.
-struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; };
-StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats = 0);
+struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; int sample_floats; };
+// `sample_floats`: 2 when the launch holds f32 stereo tracks (their tiles are staged as raw interleaved pairs), else 1.
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats = 0, int sample_floats = 1);
 
 // FFT twiddle tables for one size (host vectors -> caller uploads).
 void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);

@@ -331,6 +331,7 @@ struct TileLoc {
     int trk, t0, nfr, off0, len, len4;
     long long S0, A0;
     bool tma;
+    bool raw2; // the tile holds raw interleaved stereo f32 (2 floats per sample), summed when the first pass loads it
 };
 // `lo` is a lower bound of the track index (a CTA visits tiles, hence tracks, in rising order)
 __device__ __forceinline__ int find_track(const StftLaunch &L, int tile_id, int lo)
@@ -343,7 +344,8 @@ __device__ __forceinline__ int find_track(const StftLaunch &L, int tile_id, int 
     return lo;
 }
 // `td` may be the descriptor in global memory or the CTA's shared-memory copy of it
-__device__ __forceinline__ void locate_tile(const StftLaunch &L, int F, int tile_id, int trk, const StftTrack *td, TileLoc &o)
+__device__ __forceinline__ void locate_tile(const StftLaunch &L, int F, int tile_id, int trk, const StftTrack *td, TileLoc &o,
+                                            bool allow_raw2)
 {
     o.trk = trk;
     o.t0 = (tile_id - td->tile_begin) * L.frames_per_tile;
@@ -354,14 +356,19 @@ __device__ __forceinline__ void locate_tile(const StftLaunch &L, int F, int tile
     o.A0 = o.S0 - o.off0; // global index whose LOCAL position is 16-byte aligned: start of the staged tile
     o.len = o.off0 + (o.nfr - 1) * td->hop + F;
     o.len4 = (o.len + 3) & ~3;
-    // a tile that lies inside the track (no reflection), mono f32, 16-byte aligned: one TMA bulk copy
-    o.tma = L.staged && td->ch == 1 && td->fmt == PCM_F32 && ((reinterpret_cast<uintptr_t>(td->pcm) & 15) == 0) &&
-            o.A0 >= 0 && o.A0 + o.len4 <= td->n && o.A0 - origin >= 0 && o.A0 - origin + o.len4 <= td->avail;
+    // a tile that lies inside the track (no reflection), f32, 16-byte aligned: one TMA bulk copy -- of the samples
+    // (mono) or of the raw interleaved pairs (stereo; the channels are summed when the first pass loads them, which
+    // needs every frame of the tile to start on an even sample and twice the room)
+    const bool plain = L.staged && td->fmt == PCM_F32 && ((reinterpret_cast<uintptr_t>(td->pcm) & 15) == 0) &&
+                       o.A0 >= 0 && o.A0 + o.len4 <= td->n && o.A0 - origin >= 0 && o.A0 - origin + o.len4 <= td->avail;
+    o.raw2 = allow_raw2 && plain && td->ch == 2 && ((td->hop | o.off0) & 1) == 0 && 2 * o.len4 <= L.tile_floats;
+    o.tma = (plain && td->ch == 1) || o.raw2;
 }
 __device__ __forceinline__ void issue_tile_copy(const StftTrack *td, const TileLoc &o, float *tile, unsigned long long *mbar)
 {
-    mbar_expect_tx(mbar, (unsigned)o.len4 * 4u);
-    bulk_copy_g2s(tile, reinterpret_cast<const float *>(td->pcm) + (o.A0 - td->origin), (unsigned)o.len4 * 4u, mbar);
+    const unsigned spf = o.raw2 ? 2u : 1u; // floats per sample in the staged tile
+    mbar_expect_tx(mbar, (unsigned)o.len4 * 4u * spf);
+    bulk_copy_g2s(tile, reinterpret_cast<const float *>(td->pcm) + (o.A0 - td->origin) * spf, (unsigned)o.len4 * 4u * spf, mbar);
 }
 
 template <int LOG2H, int PTS, int V, int G, int MC> struct K1Traits {
@@ -376,7 +383,9 @@ template <int LOG2H, int PTS, int V, int G, int MC> struct K1Traits {
 // MEL: the launch projects onto a mel filterbank (MODE_MEL_DB).  A compile-time flag rather than a test of
 // L.mode: the code of the other output modes (and their branch targets) is then absent from the mel kernel's
 // instruction stream, which is long enough for instruction fetch to show up in the stall profile.
-template <int LOG2H, int PTS, int V, int G, int MC, bool MEL>
+// RAW2: f32 stereo tiles are staged as raw interleaved pairs by TMA and summed by the first pass (its own
+// instantiation: the extra first-pass variant costs the mono kernels 2 % when it merely sits in their code).
+template <int LOG2H, int PTS, int V, int G, int MC, bool MEL, bool RAW2>
 __global__ void __launch_bounds__(K1Traits<LOG2H, PTS, V, G, MC>::THREADS, MC)
 stft_db_kernel(const StftLaunch L)
 {
@@ -430,7 +439,7 @@ stft_db_kernel(const StftLaunch L)
     int trk_end = s_trk_end;
     const StftTrack *td = &s_td;
     TileLoc cur;
-    locate_tile(L, F, blockIdx.x, s_trk, td, cur);
+    locate_tile(L, F, blockIdx.x, s_trk, td, cur, RAW2);
     if (cur.tma && tid == 0) issue_tile_copy(td, cur, tile, mbar);
 
     float vmax = -INFINITY, vmin = INFINITY;
@@ -458,7 +467,7 @@ stft_db_kernel(const StftLaunch L)
             enter_track(tile_id, cur.trk);
             trk_end = s_trk_end;
         }
-        locate_tile(L, F, tile_id, s_trk, td, cur);
+        locate_tile(L, F, tile_id, s_trk, td, cur, RAW2);
     }
     if (cur.trk != range_trk) { range_trk = cur.trk; vmax = -INFINITY; vmin = INFINITY; }
     const PcmView pv{td->pcm, td->n, td->ch, td->fmt, td->origin, td->avail};
@@ -545,7 +554,7 @@ stft_db_kernel(const StftLaunch L)
         float re[PTS][V], im[PTS][V];
 
         // ---- first-pass inputs: z[m] = g[2m] + i g[2m+1], g = sample * window ---------------------
-        if (L.staged && vec_ok) {
+        if (L.staged && vec_ok && !(RAW2 && cur.raw2)) {
             // every frame of the tile starts on an even float: one 64-bit shared load per point
             const float *fb[V];
 #pragma unroll
@@ -558,6 +567,21 @@ stft_db_kernel(const StftLaunch L)
                 for (int v = 0; v < V; ++v) {
                     const float2 x = *reinterpret_cast<const float2 *>(fb[v] + 2 * p * NT);
                     re[p][v] = x.x * w.x; im[p][v] = x.y * w.y;
+                }
+            }
+        } else if (RAW2 && L.staged && vec_ok) {
+            // raw stereo tile: one 128-bit shared load brings (L, R) of two consecutive samples; lib.rs:42 sums them
+            const float *fb[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) fb[v] = tile + 2 * (off0 + min(fl0 + v, nfr - 1) * hop + 2 * gt);
+#pragma unroll
+            for (int p = 0; p < PTS; ++p) {
+                const int n = 2 * (gt + p * NT);
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(win_f + n));
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float4 x = *reinterpret_cast<const float4 *>(fb[v] + 4 * p * NT);
+                    re[p][v] = (x.x + x.y) * w.x; im[p][v] = (x.z + x.w) * w.y;
                 }
             }
         } else {
@@ -596,7 +620,7 @@ stft_db_kernel(const StftLaunch L)
                         const StftTrack *ntd = td;
                         int ntrk = cur.trk;
                         if (nt >= trk_end) { ntrk = find_track(L, nt, cur.trk); ntd = L.tracks + ntrk; }
-                        locate_tile(L, F, nt, ntrk, ntd, nx);
+                        locate_tile(L, F, nt, ntrk, ntd, nx, RAW2);
                         if (nx.tma) issue_tile_copy(ntd, nx, tile, mbar);
                     }
                 }
@@ -1220,11 +1244,11 @@ int resident_sms()
     return sms > 0 ? sms : 148;
 }
 
-template <int LOG2H, int PTS, int V, int G, int MC, bool MEL>
+template <int LOG2H, int PTS, int V, int G, int MC, bool MEL, bool RAW2>
 cudaError_t launch_one_mode(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
     using TR = K1Traits<LOG2H, PTS, V, G, MC>;
-    auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC, MEL>;
+    auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC, MEL, RAW2>;
     cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     if (e != cudaSuccess) return e;
     // persistent CTAs: as many as are resident at once, each walking tiles blockIdx.x + k gridDim.x
@@ -1236,8 +1260,11 @@ cudaError_t launch_one_mode(const StftLaunch &L, size_t smem, cudaStream_t strea
 template <int LOG2H, int PTS, int V, int G, int MC>
 cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
-    return L.mode == MODE_MEL_DB ? launch_one_mode<LOG2H, PTS, V, G, MC, true>(L, smem, stream)
-                                 : launch_one_mode<LOG2H, PTS, V, G, MC, false>(L, smem, stream);
+    // raw stereo staging exists for the mel kernels (the viewer's default scale); linear launches gather stereo tiles
+    if (L.mode == MODE_MEL_DB)
+        return L.stereo_raw ? launch_one_mode<LOG2H, PTS, V, G, MC, true, true>(L, smem, stream)
+                            : launch_one_mode<LOG2H, PTS, V, G, MC, true, false>(L, smem, stream);
+    return launch_one_mode<LOG2H, PTS, V, G, MC, false, false>(L, smem, stream);
 }
 
 } // namespace
@@ -1308,7 +1335,7 @@ size_t stft_warp_smem_bytes(int nnz, int n_mel) { return k1w_smem_bytes(nnz, n_m
 
 size_t stft_max_dynamic_smem() { return 227 * 1024; }
 
-StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats)
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, int sample_floats)
 {
     StftTiling t{};
     if (cfg.warp_per_frame) { // one "tile" per frame; nothing is staged per tile
@@ -1340,7 +1367,7 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats)
         int best = 0;
         for (int mult = 1; mult <= 8; ++mult) {
             const int nfr = unit * mult;
-            const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
+            const long need = (3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4) * sample_floats;
             if (need <= cap_floats && (want_nfr == 0 || nfr <= want_nfr || best == 0)) best = nfr;
         }
         if (best == 0 && with_bank) continue; // rather stage the tile than the taps
@@ -1350,10 +1377,11 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats)
         } else {
             t.frames_per_tile = best; t.staged = 1;
             long need = 3 + (long)(best - 1) * max_hop + cfg.n_fft;
-            t.tile_floats = (int)((need + 3) & ~3L) + 4;
+            t.tile_floats = ((int)((need + 3) & ~3L) + 4) * sample_floats;
         }
         break;
     }
+    t.sample_floats = sample_floats;
     t.smem_bytes = 16 + (size_t)(t.tile_floats + t.bank_floats) * sizeof(float) + cfg.fft_smem;
     return t;
 }
