@@ -405,9 +405,9 @@ stft_db_kernel(const StftLaunch L)
     float *sim = sre + PADH * V;
 
     // ---- persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ------------------------------------
-    // The PCM tile is only read by the first FFT pass (into registers); as soon as every group has done
-    // that, thread 0 starts the bulk copy of the CTA's NEXT tile into the same buffer, so the copy runs
-    // under the remaining passes, the split and the mel projection of the current one.
+    // The PCM tile is only read by the first FFT pass (into registers); as soon as every warp has done
+    // that, the last one to check in starts the bulk copy of the CTA's NEXT tile into the same buffer, so
+    // the copy runs under the remaining passes, the split and the mel projection of the current one.
     float *bank = fftbuf + (size_t)G * 2 * PADH * V; // dedicated filterbank region (L.bank_floats floats), if any
     const float *bank_src = nullptr;                  // whose taps it currently holds
     const int mode = MEL ? (int)MODE_MEL_DB : L.mode;
@@ -505,7 +505,7 @@ stft_db_kernel(const StftLaunch L)
         bank_src = td->mel_w;
     }
 
-    // ---- the PCM tile: landed by TMA (issued one tile ago), or gathered here (edges, stereo, int16) -----
+    // ---- the PCM tile: landed by TMA (issued one tile ago), or gathered here (edges, int16, stereo outside RAW2) -----
     if (L.staged) {
         if (cur.tma) {
             mbar_wait(mbar, phase);
