@@ -101,3 +101,19 @@ def test_wav_reader_and_errors(msv, tmp_path):
     with pytest.raises(msv.SgxError) as e:
         msv.open_audio_file(str(tmp_path / "bad.wav"))
     assert e.value.code == msv.SGX_ERR_IO
+
+
+def test_rust_sys_crate_is_in_step_with_the_header():
+    """bindings/rust/sgx-sys/src/lib.rs (uncompiled: no Rust toolchain here) is generated from include/sgx.h and
+    declares every entry point the header does."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"])
+    hdr = open(os.path.join(root, "include", "sgx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sgx_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(root, "bindings", "rust", "sgx-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (sgx_[a-z0-9_]+)\(", rs))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
