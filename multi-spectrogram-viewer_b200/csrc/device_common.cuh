@@ -49,12 +49,9 @@ struct StftLaunch {
     int tile_floats;       // capacity of the staged tile
     int bank_floats;       // > 0: the CTA keeps the track's mel taps + descriptors in a region of its own
     int stereo_raw;        // 1: the launch holds f32 stereo tracks and its tiles have room for raw interleaved pairs
+    int warp2;             // 1: tiles were planned for the warp-per-frame-pair kernel (n_fft = 2048)
     const float2 *tw;      // [h]      exp(-2 pi i j / h)
     const float2 *split;   // [h/2+1]  (cos, sin)(k pi / h)                realfft.rs:88-93
-    // warp-per-frame kernel (n_fft = 2048)
-    const float2 *tw2;         // [32][32]  W_1024^(lane k1)
-    const float2 *split_full;  // [1024]    (cos, sin)(k pi / 1024)
-    int mel_nnz, mel_rows;     // size of the shared filterbank (taps, filters) of this launch
 };
 
 // order-preserving float <-> unsigned mapping for atomicMax / atomicMin on dB values

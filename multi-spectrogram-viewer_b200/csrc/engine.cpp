@@ -85,13 +85,6 @@ FftPlan &DeviceCtx::plan(size_t n_fft)
         p->tw.alloc(h); p->split.alloc(h / 2 + 1);
         SGX_CUDA(cudaMemcpy(p->tw.p, tw.data(), sizeof(float2) * h, cudaMemcpyHostToDevice));
         SGX_CUDA(cudaMemcpy(p->split.p, sp.data(), sizeof(float2) * (h / 2 + 1), cudaMemcpyHostToDevice));
-        if (p->cfg.warp_per_frame) {
-            std::vector<float2> t2(1024), sf(1024);
-            make_warp_fft_tables(t2.data(), sf.data());
-            p->tw2.alloc(1024); p->split_full.alloc(1024);
-            SGX_CUDA(cudaMemcpy(p->tw2.p, t2.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
-            SGX_CUDA(cudaMemcpy(p->split_full.p, sf.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
-        }
     }
     it = plans_.emplace(n_fft, std::move(p)).first;
     return *it->second;
@@ -363,20 +356,15 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         if (sec > max_sec_) { max_sec_ = sec; id_max_sec_ = ids[i]; }
     }
     // ---- update_specs (lib.rs:142-168): one K1 launch per FFT size -------------------------------------
-    // tracks that share an FFT size go into one launch; the warp-per-frame kernel stages window / mel tables
-    // once per CTA, so there a launch is additionally limited to tracks sharing those tables
-    std::map<std::pair<size_t, const TrackTables *>, std::vector<size_t>> by_fft;
-    for (size_t id : ids) {
-        const Track &t = tracks_.at(id);
-        const bool per_table = ctx_->plan(t.n_fft).cfg.warp_per_frame;
-        by_fft[std::make_pair(t.n_fft, per_table ? (const TrackTables *)t.tables : nullptr)].push_back(id);
-    }
+    // tracks that share an FFT size go into one launch
+    std::map<size_t, std::vector<size_t>> by_fft;
+    for (size_t id : ids) by_fft[tracks_.at(id).n_fft].push_back(id);
     std::vector<StftTrack> descs;
     std::vector<size_t> desc_ids;
-    struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; const TrackTables *tables = nullptr; };
+    struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; };
     std::vector<Group> groups;
     for (auto &kv : by_fft) {
-        const StftConfig &cfg = ctx_->plan(kv.first.first).cfg;
+        const StftConfig &cfg = ctx_->plan(kv.first).cfg;
         int max_hop = 1;
         for (size_t id : kv.second) max_hop = std::max<int>(max_hop, (int)tracks_.at(id).hop);
         int bank_floats = 0; // room the largest filterbank of the launch needs in shared memory
@@ -390,8 +378,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
             const Track &t = tracks_.at(id);
             if (set_.freq_scale == SGX_FREQ_MEL && t.ch == 2 && t.fmt == PCM_F32) sample_floats = 2;
         }
-        Group g{kv.first.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats, sample_floats), 0};
-        g.tables = tracks_.at(kv.second.front()).tables;
+        Group g{kv.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats, sample_floats), 0};
         // a track id may appear twice in id_list; the last one wins, launch it once
         std::vector<size_t> uniq;
         for (size_t id : kv.second) if (std::find(uniq.begin(), uniq.end(), id) == uniq.end()) uniq.push_back(id);
@@ -418,9 +405,7 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
         L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
         L.tile_floats = g.tiling.tile_floats; L.bank_floats = g.tiling.bank_floats; L.tw = pl.tw.p; L.split = pl.split.p;
-        L.stereo_raw = g.tiling.sample_floats == 2 ? 1 : 0;
-        L.tw2 = pl.tw2.p; L.split_full = pl.split_full.p;
-        L.mel_nnz = g.tables ? g.tables->mel_nnz : 0; L.mel_rows = g.tables ? (int)g.tables->n_mel : 0;
+        L.stereo_raw = g.tiling.sample_floats == 2 ? 1 : 0; L.warp2 = g.tiling.warp2;
         if (!pipelined) { SGX_CUDA(launch_stft(pl.cfg, L, stream_)); continue; }
         for (size_t k = 0; k < g.count; ++k) {
             const size_t di = g.first + k;
@@ -489,10 +474,6 @@ AxisTableDev *MultiTrack::axis_table(int n_in, int n_out, bool tap_major)
     const auto key = std::make_tuple(n_in, n_out, tap_major);
     auto it = axis_.find(key);
     if (it != axis_.end()) return it->second.get();
-    if (axis_.size() >= 128) { // bounded cache; tables may be referenced by enqueued launches
-        SGX_CUDA(cudaStreamSynchronize(stream_));
-        axis_.clear();
-    }
     std::unique_ptr<AxisTableDev> t(new AxisTableDev());
     // the fast render kernels read 8 or 16 taps per output index unconditionally: rows are at least 16 wide, zero-filled
     t->taps = (std::max(16, (int)lanczos3_max_taps((uint32_t)n_in, (uint32_t)n_out)) + 3) & ~3;
@@ -513,6 +494,13 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
     if (nheight > 65535u) throw Error(SGX_ERR_BAD_ARG, "nheight too large");
     const bool mel = set_.freq_scale == SGX_FREQ_MEL;
     const uint32_t msr = effective_max_sr();
+    // The axis-table cache is bounded, but it is only ever emptied HERE, before this call resolves its first key:
+    // descriptors assembled below hold raw pointers into it (and launches already enqueued read its device tables,
+    // hence the synchronisation).  Inside a call it grows by at most two entries per track.
+    if (axis_.size() >= 128) {
+        SGX_CUDA(cudaStreamSynchronize(stream_));
+        axis_.clear();
+    }
     struct Item { size_t idx; int T, height, nwidth, cols; };
     std::vector<Item> items;
     std::vector<RenderTrack> descs;
@@ -715,9 +703,8 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     L.tracks = dd.p; L.n_tracks = 1;
     L.n_tiles = (int)(((size_t)T + tl.frames_per_tile - 1) / tl.frames_per_tile);
     L.mode = mode; L.frames_per_tile = tl.frames_per_tile; L.staged = tl.staged; L.tile_floats = tl.tile_floats;
-    L.bank_floats = tl.bank_floats;
+    L.bank_floats = tl.bank_floats; L.warp2 = tl.warp2;
     L.tw = pl.tw.p; L.split = pl.split.p;
-    L.tw2 = pl.tw2.p; L.split_full = pl.split_full.p; L.mel_nnz = tt.mel_nnz; L.mel_rows = (int)tt.n_mel;
     SGX_CUDA(launch_stft(pl.cfg, L, s));
     SGX_CUDA(cudaMemcpyAsync(out, d_out.p, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     SGX_CUDA(cudaStreamSynchronize(s));

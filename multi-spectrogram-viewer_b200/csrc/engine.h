@@ -57,7 +57,6 @@ template <class T> struct DevBuf {
 struct FftPlan {
     StftConfig cfg;
     DevBuf<float2> tw, split;
-    DevBuf<float2> tw2, split_full; // warp-per-frame kernel (n_fft = 2048)
 };
 
 // everything that depends on (sr, win, n_fft, n_mel): the `windows` / `mel_fbs` caches, lib.rs:76-77

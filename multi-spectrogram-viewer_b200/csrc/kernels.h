@@ -19,8 +19,8 @@ struct StftConfig {
     int min_ctas;          // resident CTAs per SM the kernel is compiled for
     size_t fft_smem;       // bytes of FFT exchange buffers
     bool generic;          // small-F fallback kernel (one CTA per frame)
-    bool warp_per_frame;   // n_fft = 2048: K1W, one warp per frame (persistent CTAs)
     bool fused;            // last FFT pass fused with the split: magnitudes unpadded, block-padded mel bank
+    bool warp2;            // n_fft = 2048: the warp-per-frame-pair kernel (stft_warp2_kernel.cu) is preferred when its tile fits
 };
 bool stft_config_for(size_t n_fft, StftConfig *cfg);
 size_t stft_max_dynamic_smem();
@@ -31,14 +31,16 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &launch, cudaStr
 // Chooses frames per tile / staging for a set of (hop) values sharing one FFT size.
 // `bank_floats`: shared-memory floats the largest mel filterbank of the launch needs (taps rounded up to 4, plus
 // 4 per filter for its descriptor), 0 when not a mel launch; the planner reports whether it got its own region.
-struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; int sample_floats; };
+struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; int sample_floats; int warp2; };
 // `sample_floats`: 2 when the launch holds f32 stereo tracks (their tiles are staged as raw interleaved pairs), else 1.
 StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats = 0, int sample_floats = 1);
 
+// the warp-per-frame-pair kernel (n_fft = 2048); `launch.warp2` routes launch_stft here
+cudaError_t launch_stft_warp2(const StftLaunch &launch, cudaStream_t stream);
+size_t stft_warp2_fixed_smem(int bank_floats); // shared memory besides the PCM tile
+
 // FFT twiddle tables for one size (host vectors -> caller uploads).
 void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);
-void make_warp_fft_tables(float2 *tw2 /*[1024]*/, float2 *split_full /*[1024]*/);
-size_t stft_warp_smem_bytes(int nnz, int n_mel);
 
 // K2: global dB range (lib.rs:193-209)
 cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s);

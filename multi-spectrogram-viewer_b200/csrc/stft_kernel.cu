@@ -27,164 +27,18 @@
 
 #include "device_common.cuh"
 #include "kernels.h"
+#include "stft_device.cuh"
+
+// The instantiations of K1 are spread over several translation units so that they compile in parallel (the Makefile
+// builds this file once per part with -DSGX_K1_PART=k; part 0 holds the host side and the generic kernel, part k > 0
+// the table rows tagged k).  Without the macro the file is one self-contained translation unit.
+#ifndef SGX_K1_PART
+#define SGX_K1_PART -1
+#endif
 
 namespace sgx {
 
 namespace {
-
-__device__ __forceinline__ int padi(int e) { return e + (e >> 3); }
-
-template <int V> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[V])
-{
-    if constexpr (V == 4) {
-        const float4 t = *reinterpret_cast<const float4 *>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else if constexpr (V == 2) {
-        const float2 t = *reinterpret_cast<const float2 *>(p);
-        v[0] = t.x; v[1] = t.y;
-    } else {
-        v[0] = *p;
-    }
-}
-template <int V> __device__ __forceinline__ void st_vec(float *p, const float (&v)[V])
-{
-    if constexpr (V == 4) {
-        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if constexpr (V == 2) {
-        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
-    } else {
-        *p = v[0];
-    }
-}
-
-// sqrt.approx.f32: max relative error 2^-23 (PTX ISA) -- one MUFU instead of the IEEE sequence
-__device__ __forceinline__ float sqrt_approx(float x)
-{
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// ---- mbarrier / TMA bulk copy (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS) ----------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p)
-{
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes,
-                                              unsigned long long *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    // try_wait suspends the thread for a hardware-defined time slice per attempt; a copy that never completes
-    // (it cannot, unless the descriptor table is corrupt) traps instead of hanging the GPU
-    for (unsigned spins = 0;; ++spins) {
-        unsigned done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (spins > (1u << 26)) __trap();
-    }
-}
-
-// ---- sample access: channel sum + reflect (lib.rs:42, utils.rs:79-85) ---------------------------
-struct PcmView {
-    const void *pcm; long long n; int ch; int fmt;
-    long long origin, avail; // time slices: pcm[0] is global sample `origin`, `avail` samples are present
-};
-__device__ __forceinline__ float load_sample(const PcmView &pv, long long i)
-{
-    if (i < 0) i = -i;                         // left reflect, edge sample not repeated
-    if (i >= pv.n) i = 2 * (pv.n - 1) - i;     // right reflect
-    i = i < 0 ? 0 : (i >= pv.n ? pv.n - 1 : i); // only reachable under zero window weight
-    i -= pv.origin;                            // global -> local index of a time slice
-    i = i < 0 ? 0 : (i >= pv.avail ? pv.avail - 1 : i);
-    float s = 0.0f;
-    if (pv.fmt == PCM_F32) {
-        const float *p = reinterpret_cast<const float *>(pv.pcm) + i * pv.ch;
-        for (int c = 0; c < pv.ch; ++c) s += __ldg(p + c);
-    } else {
-        const short *p = reinterpret_cast<const short *>(pv.pcm) + i * pv.ch;
-        for (int c = 0; c < pv.ch; ++c) s += (float)__ldg(p + c) * (1.0f / 32768.0f); // audio.rs:16-19
-    }
-    return s;
-}
-
-// ---- in-register DFT of R points at re[BASE + i*STRIDE], natural order in and out ----------------
-// cos/sin(2 pi k / 32), k < 16
-__device__ constexpr float kC32[16] = {
-    1.0f, 0.98078528040323044f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
-    0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f, -0.19509032201612825f,
-    -0.38268343236508977f, -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
-    -0.92387953251128674f, -0.98078528040323044f};
-__device__ constexpr float kS32[16] = {
-    0.0f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f, 0.70710678118654752f,
-    0.83146961230254524f, 0.92387953251128674f, 0.98078528040323044f, 1.0f, 0.98078528040323044f,
-    0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
-    0.38268343236508977f, 0.19509032201612825f};
-
-template <int R, int BASE, int STRIDE, int PTS, int V>
-__device__ __forceinline__ void dft_inplace(float (&re)[PTS][V], float (&im)[PTS][V])
-{
-    if constexpr (R == 2) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const float ar = re[BASE][v], ai = im[BASE][v];
-            const float br = re[BASE + STRIDE][v], bi = im[BASE + STRIDE][v];
-            re[BASE][v] = ar + br; im[BASE][v] = ai + bi;
-            re[BASE + STRIDE][v] = ar - br; im[BASE + STRIDE][v] = ai - bi;
-        }
-    } else if constexpr (R > 2) {
-        dft_inplace<R / 2, BASE, 2 * STRIDE, PTS, V>(re, im);          // even inputs
-        dft_inplace<R / 2, BASE + STRIDE, 2 * STRIDE, PTS, V>(re, im); // odd inputs
-        float tr[R][V], ti[R][V];
-#pragma unroll
-        for (int k = 0; k < R / 2; ++k) {
-            const int e = BASE + 2 * k * STRIDE, o = BASE + (2 * k + 1) * STRIDE;
-            const int widx = k * (32 / R); // exp(-2 pi i k / R) = kC32[widx] - i kS32[widx]
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                float pr, pi;
-                if (widx == 0) { pr = re[o][v]; pi = im[o][v]; }
-                else if (widx == 8) { pr = im[o][v]; pi = -re[o][v]; }
-                else {
-                    const float c = kC32[widx], s = kS32[widx];
-                    pr = re[o][v] * c + im[o][v] * s;
-                    pi = im[o][v] * c - re[o][v] * s;
-                }
-                tr[k][v] = re[e][v] + pr; ti[k][v] = im[e][v] + pi;
-                tr[k + R / 2][v] = re[e][v] - pr; ti[k + R / 2][v] = im[e][v] - pi;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-#pragma unroll
-            for (int v = 0; v < V; ++v) { re[BASE + k * STRIDE][v] = tr[k][v]; im[BASE + k * STRIDE][v] = ti[k][v]; }
-    }
-}
 
 // ---- one Stockham pass of radix R with NS = product of the previous radices ----------------------
 // Thread `gt` of the group owns butterflies j = gt + q*NT, q < PTS/R.  Inputs of butterfly j are
@@ -198,9 +52,10 @@ template <int G, int NT> __device__ __forceinline__ void group_sync(int grp)
 }
 
 template <int H, int PTS, int V, int G, int R, int NS>
-__device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V], float *sre,
+__device__ __forceinline__ void fft_pass(pk (&re)[PTS][V / 2], pk (&im)[PTS][V / 2], float *sre,
                                          float *sim, int gt, int grp, const float2 *__restrict__ tw)
 {
+    constexpr int VP = V / 2;
     constexpr int NT = H / PTS, NB = PTS / R;
     if constexpr (NS > 1) {
         // twiddle bases first: the table loads fly while the shared loads and the barrier complete
@@ -215,8 +70,8 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int src = sbase + ((q * NT + r * (H / R)) / 8 * 9) * V;
-                ld_vec<V>(sre + src, re[q * R + r]);
-                ld_vec<V>(sim + src, im[q * R + r]);
+                ld_vec<VP>(sre + src, re[q * R + r]);
+                ld_vec<VP>(sim + src, im[q * R + r]);
             }
         group_sync<G, NT>(grp); // every thread has its inputs: the buffer may be overwritten
 #pragma unroll
@@ -245,25 +100,25 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
 #pragma unroll
             for (int r = 1; r < R; ++r) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const float xr = re[q * R + r][v], xi = im[q * R + r][v];
-                    re[q * R + r][v] = xr * w[r].x - xi * w[r].y;
-                    im[q * R + r][v] = xr * w[r].y + xi * w[r].x;
+                for (int v = 0; v < VP; ++v) {
+                    const pk xr = re[q * R + r][v], xi = im[q * R + r][v];
+                    re[q * R + r][v] = pk_fmas(xi, -w[r].y, pk_muls(xr, w[r].x));
+                    im[q * R + r][v] = pk_fmas(xi, w[r].x, pk_muls(xr, w[r].y));
                 }
             }
         }
     }
-    if constexpr (NB == 1) dft_inplace<R, 0, 1, PTS, V>(re, im);
-    else if constexpr (NB == 2) { dft_inplace<R, 0, 1, PTS, V>(re, im); dft_inplace<R, R, 1, PTS, V>(re, im); }
+    if constexpr (NB == 1) dft_inplace<R, 0, 1, PTS, VP>(re, im);
+    else if constexpr (NB == 2) { dft_inplace<R, 0, 1, PTS, VP>(re, im); dft_inplace<R, R, 1, PTS, VP>(re, im); }
     else if constexpr (NB == 4) {
-        dft_inplace<R, 0, 1, PTS, V>(re, im); dft_inplace<R, R, 1, PTS, V>(re, im);
-        dft_inplace<R, 2 * R, 1, PTS, V>(re, im); dft_inplace<R, 3 * R, 1, PTS, V>(re, im);
+        dft_inplace<R, 0, 1, PTS, VP>(re, im); dft_inplace<R, R, 1, PTS, VP>(re, im);
+        dft_inplace<R, 2 * R, 1, PTS, VP>(re, im); dft_inplace<R, 3 * R, 1, PTS, VP>(re, im);
     } else {
         static_assert(NB == 8, "unsupported butterflies per thread");
-        dft_inplace<R, 0, 1, PTS, V>(re, im); dft_inplace<R, R, 1, PTS, V>(re, im);
-        dft_inplace<R, 2 * R, 1, PTS, V>(re, im); dft_inplace<R, 3 * R, 1, PTS, V>(re, im);
-        dft_inplace<R, 4 * R, 1, PTS, V>(re, im); dft_inplace<R, 5 * R, 1, PTS, V>(re, im);
-        dft_inplace<R, 6 * R, 1, PTS, V>(re, im); dft_inplace<R, 7 * R, 1, PTS, V>(re, im);
+        dft_inplace<R, 0, 1, PTS, VP>(re, im); dft_inplace<R, R, 1, PTS, VP>(re, im);
+        dft_inplace<R, 2 * R, 1, PTS, VP>(re, im); dft_inplace<R, 3 * R, 1, PTS, VP>(re, im);
+        dft_inplace<R, 4 * R, 1, PTS, VP>(re, im); dft_inplace<R, 5 * R, 1, PTS, VP>(re, im);
+        dft_inplace<R, 6 * R, 1, PTS, VP>(re, im); dft_inplace<R, 7 * R, 1, PTS, VP>(re, im);
     }
     if constexpr (NS == 1 && R == 8) {
         // d = 8 j, element 8 j + r -> padded 9 j + r
@@ -272,8 +127,8 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int dst = (9 * gt + 9 * q * NT + r) * V;
-                st_vec<V>(sre + dst, re[q * R + r]);
-                st_vec<V>(sim + dst, im[q * R + r]);
+                st_vec<VP>(sre + dst, re[q * R + r]);
+                st_vec<VP>(sim + dst, im[q * R + r]);
             }
     } else if constexpr (NS % 8 == 0) {
         // k = j mod NS is the same for every q when NS divides NT; when NS > NT, j < NS and d = j.
@@ -286,8 +141,8 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int dst = dbase + (((kSmall ? q * NT * R : q * NT) + r * NS) / 8 * 9) * V;
-                st_vec<V>(sre + dst, re[q * R + r]);
-                st_vec<V>(sim + dst, im[q * R + r]);
+                st_vec<VP>(sre + dst, re[q * R + r]);
+                st_vec<VP>(sim + dst, im[q * R + r]);
             }
     } else {
 #pragma unroll
@@ -298,8 +153,8 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int dst = padi(d + r * NS) * V;
-                st_vec<V>(sre + dst, re[q * R + r]);
-                st_vec<V>(sim + dst, im[q * R + r]);
+                st_vec<VP>(sre + dst, re[q * R + r]);
+                st_vec<VP>(sim + dst, im[q * R + r]);
             }
         }
     }
@@ -308,7 +163,7 @@ __device__ __forceinline__ void fft_pass(float (&re)[PTS][V], float (&im)[PTS][V
 
 // Runs the passes whose input stride product NS is below NS_END (H: all passes).
 template <int H, int PTS, int V, int G, int NS, int NS_END>
-__device__ __forceinline__ void run_passes(float (&re)[PTS][V], float (&im)[PTS][V], float *sre,
+__device__ __forceinline__ void run_passes(pk (&re)[PTS][V / 2], pk (&im)[PTS][V / 2], float *sre,
                                            float *sim, int gt, int grp, const float2 *__restrict__ tw)
 {
     if constexpr (NS < NS_END) {
@@ -324,51 +179,6 @@ __host__ __device__ constexpr int last_radix(int h, int pts)
     int n = h;
     while (n >= pts) n /= pts;
     return n > 1 ? n : pts;
-}
-
-// Where one CTA tile of a launch lives: its track, its frames and the PCM span they read.
-struct TileLoc {
-    int trk, t0, nfr, off0, len, len4;
-    long long S0, A0;
-    bool tma;
-    bool raw2; // the tile holds raw interleaved stereo f32 (2 floats per sample), summed when the first pass loads it
-};
-// `lo` is a lower bound of the track index (a CTA visits tiles, hence tracks, in rising order)
-__device__ __forceinline__ int find_track(const StftLaunch &L, int tile_id, int lo)
-{
-    int hi = L.n_tracks - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (L.tracks[mid].tile_begin <= tile_id) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-// `td` may be the descriptor in global memory or the CTA's shared-memory copy of it
-__device__ __forceinline__ void locate_tile(const StftLaunch &L, int F, int tile_id, int trk, const StftTrack *td, TileLoc &o,
-                                            bool allow_raw2)
-{
-    o.trk = trk;
-    o.t0 = (tile_id - td->tile_begin) * L.frames_per_tile;
-    o.nfr = min(L.frames_per_tile, td->n_frames - o.t0);
-    const long long origin = td->origin;
-    o.S0 = (long long)(td->frame0 + o.t0) * td->hop - td->win / 2 - td->pad_l; // first (global) sample of the tile's first FFT frame
-    o.off0 = (int)((o.S0 - origin) & 3);
-    o.A0 = o.S0 - o.off0; // global index whose LOCAL position is 16-byte aligned: start of the staged tile
-    o.len = o.off0 + (o.nfr - 1) * td->hop + F;
-    o.len4 = (o.len + 3) & ~3;
-    // a tile that lies inside the track (no reflection), f32, 16-byte aligned: one TMA bulk copy -- of the samples
-    // (mono) or of the raw interleaved pairs (stereo; the channels are summed when the first pass loads them, which
-    // needs every frame of the tile to start on an even sample and twice the room)
-    const bool plain = L.staged && td->fmt == PCM_F32 && ((reinterpret_cast<uintptr_t>(td->pcm) & 15) == 0) &&
-                       o.A0 >= 0 && o.A0 + o.len4 <= td->n && o.A0 - origin >= 0 && o.A0 - origin + o.len4 <= td->avail;
-    o.raw2 = allow_raw2 && plain && td->ch == 2 && ((td->hop | o.off0) & 1) == 0 && 2 * o.len4 <= L.tile_floats;
-    o.tma = (plain && td->ch == 1) || o.raw2;
-}
-__device__ __forceinline__ void issue_tile_copy(const StftTrack *td, const TileLoc &o, float *tile, unsigned long long *mbar)
-{
-    const unsigned spf = o.raw2 ? 2u : 1u; // floats per sample in the staged tile
-    mbar_expect_tx(mbar, (unsigned)o.len4 * 4u * spf);
-    bulk_copy_g2s(tile, reinterpret_cast<const float *>(td->pcm) + (o.A0 - td->origin) * spf, (unsigned)o.len4 * 4u * spf, mbar);
 }
 
 template <int LOG2H, int PTS, int V, int G, int MC> struct K1Traits {
@@ -551,7 +361,8 @@ stft_db_kernel(const StftLaunch L)
     for (int it = 0; it < iters; ++it) {
         if (it * G * V >= nfr) break; // uniform
         const int fl0 = (it * G + grp) * V; // first local frame of this group
-        float re[PTS][V], im[PTS][V];
+        constexpr int VP = V / 2;
+        pk re[PTS][VP], im[PTS][VP]; // pair i = frames 2i, 2i+1 of the group
 
         // ---- first-pass inputs: z[m] = g[2m] + i g[2m+1], g = sample * window ---------------------
         if (L.staged && vec_ok && !(RAW2 && cur.raw2)) {
@@ -566,7 +377,7 @@ stft_db_kernel(const StftLaunch L)
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const float2 x = *reinterpret_cast<const float2 *>(fb[v] + 2 * p * NT);
-                    re[p][v] = x.x * w.x; im[p][v] = x.y * w.y;
+                    pk_set<VP>(re[p], v, x.x * w.x); pk_set<VP>(im[p], v, x.y * w.y);
                 }
             }
         } else if (RAW2 && L.staged && vec_ok) {
@@ -581,7 +392,7 @@ stft_db_kernel(const StftLaunch L)
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const float4 x = *reinterpret_cast<const float4 *>(fb[v] + 4 * p * NT);
-                    re[p][v] = (x.x + x.y) * w.x; im[p][v] = (x.z + x.w) * w.y;
+                    pk_set<VP>(re[p], v, (x.x + x.y) * w.x); pk_set<VP>(im[p], v, (x.z + x.w) * w.y);
                 }
             }
         } else {
@@ -600,7 +411,7 @@ stft_db_kernel(const StftLaunch L)
                         const long long i = S0 + (long long)fl * hop + n;
                         x0 = load_sample(pv, i); x1 = load_sample(pv, i + 1);
                     }
-                    re[p][v] = x0 * w.x; im[p][v] = x1 * w.y;
+                    pk_set<VP>(re[p], v, x0 * w.x); pk_set<VP>(im[p], v, x1 * w.y);
                 }
             }
         }
@@ -629,26 +440,29 @@ stft_db_kernel(const StftLaunch L)
         // ---- real-FFT split (realfft.rs:140-157) -------------------------------------------------------
         // emit(): what becomes of one output bin -- complex / magnitude / dB to HBM, or (mel) its
         // magnitude into the shared buffer at the bin's own (padded) position.
-        auto emit = [&](int idx, int spos, const float (&xr)[V], const float (&xi)[V]) {
+        auto emit = [&](int idx, int spos, const pk (&xr)[VP], const pk (&xi)[VP]) {
             if (mode == MODE_COMPLEX) {
 #pragma unroll
                 for (int v = 0; v < V; ++v)
                     if (fl0 + v < nfr)
                         reinterpret_cast<float2 *>(out)[(size_t)(t0 + fl0 + v) * (H + 1) + idx] =
-                            make_float2(xr[v], xi[v]);
+                            make_float2(pk_get<VP>(xr, v), pk_get<VP>(xi, v));
                 return;
             }
-            float mg[V];
+            pk mg[VP];
 #pragma unroll
-            for (int v = 0; v < V; ++v) mg[v] = sqrt_approx(fmaf(xr[v], xr[v], xi[v] * xi[v])); // lib.rs:124
+            for (int v = 0; v < VP; ++v) { // lib.rs:124
+                const pk q = pk_fma(xr[v], xr[v], pk_mul(xi[v], xi[v]));
+                mg[v] = make_float2(sqrt_approx(q.x), sqrt_approx(q.y));
+            }
             if (MEL) {
-                st_vec<V>(sre + (melp ? idx * V : spos), mg); // block-padded bank: magnitudes at their bin index
+                st_vec<VP>(sre + (melp ? idx * V : spos), mg); // block-padded bank: magnitudes at their bin index
             } else {
                 // frames beyond the tile's last one are copies of it (first-pass clamp): harmless in the extrema
                 float *op = out + (size_t)(t0 + fl0) * (H + 1) + idx;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    float y = mg[v];
+                    float y = pk_get<VP>(mg, v);
                     if (mode == MODE_LIN_DB) {
                         y = amp_to_db_dev(y);
                         vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
@@ -659,17 +473,17 @@ stft_db_kernel(const StftLaunch L)
         };
 
         // one conjugate-symmetric pair: a = Z[k], b = Z[h-k], k <= h/2 -> X[k] and (optionally) X[h-k]
-        auto split_pair = [&](int k, float2 cs, const float (&ar)[V], const float (&ai)[V], const float (&br)[V],
-                              const float (&bi)[V], bool emit_partner) {
-            float xr[V], xi[V], yr[V], yi[V];
+        auto split_pair = [&](int k, float2 cs, const pk (&ar)[VP], const pk (&ai)[VP], const pk (&br)[VP],
+                              const pk (&bi)[VP], bool emit_partner) {
+            pk xr[VP], xi[VP], yr[VP], yi[VP];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const float sumr = ar[v] + br[v], difr = ar[v] - br[v];
-                const float sumi = ai[v] + bi[v], difi = ai[v] - bi[v];
-                const float p1 = fmaf(cs.x, sumi, -cs.y * difr);  // c*sumi - s*difr
-                const float p2 = fmaf(cs.y, sumi, cs.x * difr);   // s*sumi + c*difr
-                xr[v] = 0.5f * (sumr + p1); xi[v] = 0.5f * (difi - p2);
-                yr[v] = 0.5f * (sumr - p1); yi[v] = -0.5f * (difi + p2);
+            for (int v = 0; v < VP; ++v) {
+                const pk sumr = pk_add(ar[v], br[v]), difr = pk_sub(ar[v], br[v]);
+                const pk sumi = pk_add(ai[v], bi[v]), difi = pk_sub(ai[v], bi[v]);
+                const pk p1 = pk_fmas(sumi, cs.x, pk_muls(difr, -cs.y));  // c*sumi - s*difr
+                const pk p2 = pk_fmas(sumi, cs.y, pk_muls(difr, cs.x));   // s*sumi + c*difr
+                xr[v] = pk_muls(pk_add(sumr, p1), 0.5f); xi[v] = pk_muls(pk_sub(difi, p2), 0.5f);
+                yr[v] = pk_muls(pk_sub(sumr, p1), 0.5f); yi[v] = pk_muls(pk_add(difi, p2), -0.5f);
             }
             emit(k, padi(k) * V, xr, xi);
             if (emit_partner) { const int kp = k == 0 ? H : H - k; emit(kp, padi(kp) * V, yr, yi); } // k == 0: Nyquist bin
@@ -707,10 +521,10 @@ stft_db_kernel(const StftLaunch L)
                 const int sa = padi(bA[p]) * V, sb = padi(bB[p]) * V;
 #pragma unroll
                 for (int r = 0; r < RL; ++r) {
-                    ld_vec<V>(sre + sa + (r * NSL / 8 * 9) * V, re[(2 * p) * RL + r]);
-                    ld_vec<V>(sim + sa + (r * NSL / 8 * 9) * V, im[(2 * p) * RL + r]);
-                    ld_vec<V>(sre + sb + (r * NSL / 8 * 9) * V, re[(2 * p + 1) * RL + r]);
-                    ld_vec<V>(sim + sb + (r * NSL / 8 * 9) * V, im[(2 * p + 1) * RL + r]);
+                    ld_vec<VP>(sre + sa + (r * NSL / 8 * 9) * V, re[(2 * p) * RL + r]);
+                    ld_vec<VP>(sim + sa + (r * NSL / 8 * 9) * V, im[(2 * p) * RL + r]);
+                    ld_vec<VP>(sre + sb + (r * NSL / 8 * 9) * V, re[(2 * p + 1) * RL + r]);
+                    ld_vec<VP>(sim + sb + (r * NSL / 8 * 9) * V, im[(2 * p + 1) * RL + r]);
                 }
             }
             if (MEL) group_sync<G, NT>(grp); // the buffer now becomes the magnitude array
@@ -726,16 +540,16 @@ stft_db_kernel(const StftLaunch L)
 #pragma unroll
                 for (int r = 1; r < RL; ++r)
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const float xr = re[b * RL + r][v], xi = im[b * RL + r][v];
-                        re[b * RL + r][v] = xr * w[r].x - xi * w[r].y;
-                        im[b * RL + r][v] = xr * w[r].y + xi * w[r].x;
+                    for (int v = 0; v < VP; ++v) {
+                        const pk xr = re[b * RL + r][v], xi = im[b * RL + r][v];
+                        re[b * RL + r][v] = pk_fmas(xi, -w[r].y, pk_muls(xr, w[r].x));
+                        im[b * RL + r][v] = pk_fmas(xi, w[r].x, pk_muls(xr, w[r].y));
                     }
             }
-            if constexpr (NPR >= 1) { dft_inplace<RL, 0, 1, PTS, V>(re, im); dft_inplace<RL, RL, 1, PTS, V>(re, im); }
-            if constexpr (NPR >= 2) { dft_inplace<RL, 2 * RL, 1, PTS, V>(re, im); dft_inplace<RL, 3 * RL, 1, PTS, V>(re, im); }
-            if constexpr (NPR >= 3) { dft_inplace<RL, 4 * RL, 1, PTS, V>(re, im); dft_inplace<RL, 5 * RL, 1, PTS, V>(re, im); }
-            if constexpr (NPR >= 4) { dft_inplace<RL, 6 * RL, 1, PTS, V>(re, im); dft_inplace<RL, 7 * RL, 1, PTS, V>(re, im); }
+            if constexpr (NPR >= 1) { dft_inplace<RL, 0, 1, PTS, VP>(re, im); dft_inplace<RL, RL, 1, PTS, VP>(re, im); }
+            if constexpr (NPR >= 2) { dft_inplace<RL, 2 * RL, 1, PTS, VP>(re, im); dft_inplace<RL, 3 * RL, 1, PTS, VP>(re, im); }
+            if constexpr (NPR >= 3) { dft_inplace<RL, 4 * RL, 1, PTS, VP>(re, im); dft_inplace<RL, 5 * RL, 1, PTS, VP>(re, im); }
+            if constexpr (NPR >= 4) { dft_inplace<RL, 6 * RL, 1, PTS, VP>(re, im); dft_inplace<RL, 7 * RL, 1, PTS, VP>(re, im); }
             static_assert(NPR <= 4, "unsupported butterfly pairs per thread");
 #pragma unroll
             for (int p = 0; p < NPR; ++p) {
@@ -748,24 +562,24 @@ stft_db_kernel(const StftLaunch L)
                 const bool self = p == 0 && gt == 0;
 #pragma unroll
                 for (int r = 0; r < RL / 2; ++r) {
-                    float pr[V], pi[V];
+                    pk pr[VP], pi[VP];
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
+                    for (int v = 0; v < VP; ++v) {
                         pr[v] = re[bb + RL - 1 - r][v]; pi[v] = im[bb + RL - 1 - r][v];
                         if (p == 0 && self) { pr[v] = re[ba + (r == 0 ? 0 : RL - r)][v]; pi[v] = im[ba + (r == 0 ? 0 : RL - r)][v]; }
                     }
                     split_pair(bA[p] + r * NSL, csA[p][r], re[ba + r], im[ba + r], pr, pi, true);
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
+                    for (int v = 0; v < VP; ++v) {
                         pr[v] = re[ba + RL - 1 - r][v]; pi[v] = im[ba + RL - 1 - r][v];
                         if (p == 0 && self) { pr[v] = re[bb + RL - 1 - r][v]; pi[v] = im[bb + RL - 1 - r][v]; }
                     }
                     split_pair(bB[p] + r * NSL, csB[p][r], re[bb + r], im[bb + r], pr, pi, true);
                 }
                 if (p == 0 && self) { // X[H/2] = conj(Z[H/2])
-                    float ni[V];
+                    pk ni[VP];
 #pragma unroll
-                    for (int v = 0; v < V; ++v) ni[v] = -im[ba + RL / 2][v];
+                    for (int v = 0; v < VP; ++v) ni[v] = pk_neg(im[ba + RL / 2][v]);
                     emit(H / 2, padi(H / 2) * V, re[ba + RL / 2], ni);
                 }
             }
@@ -780,28 +594,28 @@ stft_db_kernel(const StftLaunch L)
             const int pa = pa0 + (q * NT / 8 * 9) * V;
             const int pbm = pb0 - (q * NT / 8 * 9) * V;     // where the partner's magnitude goes (index H when k == 0)
             const int pb = (q == 0 && gt == 0) ? 0 : pbm;   // where the partner's spectrum is read (index 0 when k == 0)
-            float ar[V], ai[V], br[V], bi[V];
-            ld_vec<V>(sre + pa, ar); ld_vec<V>(sim + pa, ai);
-            ld_vec<V>(sre + pb, br); ld_vec<V>(sim + pb, bi);
+            pk ar[VP], ai[VP], br[VP], bi[VP];
+            ld_vec<VP>(sre + pa, ar); ld_vec<VP>(sim + pa, ai);
+            ld_vec<VP>(sre + pb, br); ld_vec<VP>(sim + pb, bi);
             const float2 cs = __ldg(L.split + k); // (cos, sin)(k pi / h)
-            float xr[V], xi[V], yr[V], yi[V];
+            pk xr[VP], xi[VP], yr[VP], yi[VP];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const float sumr = ar[v] + br[v], difr = ar[v] - br[v];
-                const float sumi = ai[v] + bi[v], difi = ai[v] - bi[v];
-                const float p1 = fmaf(cs.x, sumi, -cs.y * difr);  // c*sumi - s*difr
-                const float p2 = fmaf(cs.y, sumi, cs.x * difr);   // s*sumi + c*difr
-                xr[v] = 0.5f * (sumr + p1); xi[v] = 0.5f * (difi - p2);
-                yr[v] = 0.5f * (sumr - p1); yi[v] = -0.5f * (difi + p2);
+            for (int v = 0; v < VP; ++v) {
+                const pk sumr = pk_add(ar[v], br[v]), difr = pk_sub(ar[v], br[v]);
+                const pk sumi = pk_add(ai[v], bi[v]), difi = pk_sub(ai[v], bi[v]);
+                const pk p1 = pk_fmas(sumi, cs.x, pk_muls(difr, -cs.y));  // c*sumi - s*difr
+                const pk p2 = pk_fmas(sumi, cs.y, pk_muls(difr, cs.x));   // s*sumi + c*difr
+                xr[v] = pk_muls(pk_add(sumr, p1), 0.5f); xi[v] = pk_muls(pk_sub(difi, p2), 0.5f);
+                yr[v] = pk_muls(pk_sub(sumr, p1), 0.5f); yi[v] = pk_muls(pk_add(difi, p2), -0.5f);
             }
             emit(k, pa, xr, xi);
             emit(k == 0 ? H : H - k, pbm, yr, yi); // k == 0: the partner output is the Nyquist bin
         }
         if (gt == 0) {
-            float cr[V], ci[V];
-            ld_vec<V>(sre + padi(H / 2) * V, cr); ld_vec<V>(sim + padi(H / 2) * V, ci);
+            pk cr[VP], ci[VP];
+            ld_vec<VP>(sre + padi(H / 2) * V, cr); ld_vec<VP>(sim + padi(H / 2) * V, ci);
 #pragma unroll
-            for (int v = 0; v < V; ++v) ci[v] = -ci[v];
+            for (int v = 0; v < VP; ++v) ci[v] = pk_neg(ci[v]);
             emit(H / 2, padi(H / 2) * V, cr, ci);
         }
         } // !FUSED
@@ -834,20 +648,23 @@ stft_db_kernel(const StftLaunch L)
                 const int m = (int)((unsigned)li >> 16), pl = lane & (P - 1);
                 const float *wp = wb + bd.x + lane;
                 const float *mp = sre + (li & 0xffff) * V;
-                float acc[V];
+                pk accp[VP];
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+                for (int v = 0; v < VP; ++v) accp[v] = make_float2(0.0f, 0.0f);
                 for (int j4 = 0; j4 < bd.y; j4 += 4) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float wgt = wp[(j4 + u) * 32];
-                        float mg[V];
-                        ld_vec<V>(mp, mg);
+                        pk mg[VP];
+                        ld_vec<VP>(mp, mg);
                         mp += stride;
 #pragma unroll
-                        for (int v = 0; v < V; ++v) acc[v] = fmaf(mg[v], wgt, acc[v]);
+                        for (int v = 0; v < VP; ++v) accp[v] = pk_fmas(mg[v], wgt, accp[v]);
                     }
                 }
+                float acc[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = pk_get<VP>(accp, v);
                 for (int sh = P >> 1; sh > 0; sh >>= 1)
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], sh);
@@ -892,19 +709,22 @@ stft_db_kernel(const StftLaunch L)
                 const int njmax = __reduce_max_sync(0xffffffffu, nj);
                 const float *wp = (ST ? wsm : mw) + mt.z + pl;
                 const int bin0 = mt.x + pl;
-                float acc[V];
+                pk accp[VP];
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+                for (int v = 0; v < VP; ++v) accp[v] = make_float2(0.0f, 0.0f);
 #pragma unroll 8
                 for (int j = 0; j < njmax; ++j) {
                     const bool on = j < nj;
                     float wgt = 0.0f;
                     if (on) wgt = ST ? wp[j << lg] : __ldg(wp + (j << lg));
-                    float mg[V];
-                    ld_vec<V>(sre + padi(on ? bin0 + (j << lg) : 0) * V, mg);
+                    pk mg[VP];
+                    ld_vec<VP>(sre + padi(on ? bin0 + (j << lg) : 0) * V, mg);
 #pragma unroll
-                    for (int v = 0; v < V; ++v) acc[v] = fmaf(mg[v], wgt, acc[v]);
+                    for (int v = 0; v < VP; ++v) accp[v] = pk_fmas(mg[v], wgt, accp[v]);
                 }
+                float acc[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = pk_get<VP>(accp, v);
                 for (int s = P >> 1; s > 0; s >>= 1)
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], s);
@@ -931,214 +751,7 @@ stft_db_kernel(const StftLaunch L)
     flush_range();
 }
 
-// =====================================================================================================
-// K1W -- warp-per-frame variant of the fused analysis kernel for n_fft = 2048 (h = 1024 = 32 x 32).
-//
-// One warp owns one frame: lane m2 first holds the 32 points z[32 m1 + m2] and runs a 32-point DFT in
-// registers, the twiddle W_1024^(m2 k1) is applied, one transpose through a private 8.25 KB shared
-// buffer re-distributes the data so that lane k1 holds A[k1][m2] for all m2, and a second in-register
-// 32-point DFT yields Z[k1 + 32 k2].  The conjugate partner of bin k1 + 32 k2 lives in lane 32 - k1,
-// register 31 - k2, so the real-FFT split is one pair of warp shuffles per bin.  No block barrier
-// exists on the frame path (16 independent warps per SM hide each other's latencies) and the spectrum
-// crosses shared memory once instead of three times.  Frames are read straight from global memory
-// with coalesced 64-bit loads; the 4x overlap between neighbouring frames -- which neighbouring warps
-// of the same CTA process at the same time -- is served by L1.  Window, twiddle, split and mel tables
-// are staged in shared memory once per (persistent) CTA.
-// =====================================================================================================
-constexpr int kWH = 1024;             // complex points
-constexpr int kWWarps = 16;
-constexpr int kWThreads = kWWarps * 32;
-constexpr int kWXchg = 32 * 33;       // float2 elements of one warp's transpose buffer (pitch 33)
-
-__host__ __device__ inline size_t k1w_smem_bytes(int nnz, int n_mel)
-{
-    return (size_t)kWWarps * kWXchg * sizeof(float2) + 2048 * sizeof(float) + 2 * kWH * sizeof(float2) +
-           (size_t)(((nnz + 3) & ~3) + 64) * sizeof(float) + (size_t)n_mel * sizeof(int4) + 16;
-}
-
-__global__ void __launch_bounds__(kWThreads, 1) stft_warp_kernel(const StftLaunch L, int nnz, int n_mel_tab)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2 *xall = reinterpret_cast<float2 *>(smem_raw);
-    float *win_s = reinterpret_cast<float *>(xall + kWWarps * kWXchg);
-    float2 *tw2_s = reinterpret_cast<float2 *>(win_s + 2048);
-    float2 *spl_s = tw2_s + kWH;
-    float *wts_s = reinterpret_cast<float *>(spl_s + kWH);
-    int4 *meta_s = reinterpret_cast<int4 *>(wts_s + ((nnz + 3) & ~3) + 64);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int mode = L.mode;
-    // ---- tables (all tracks of a launch share them; the host groups launches accordingly) --------------
-    {
-        const StftTrack *__restrict__ t0 = L.tracks;
-        for (int i = tid; i < 2048; i += kWThreads) win_s[i] = __ldg(t0->win_f + i);
-        for (int i = tid; i < kWH; i += kWThreads) { tw2_s[i] = __ldg(L.tw2 + i); spl_s[i] = __ldg(L.split_full + i); }
-        if (mode == MODE_MEL_DB) {
-            for (int i = tid; i < ((nnz + 3) & ~3) + 64; i += kWThreads) wts_s[i] = i < nnz ? __ldg(t0->mel_w + i) : 0.0f;
-            const int4 *__restrict__ meta = reinterpret_cast<const int4 *>(t0->mel_lo);
-            for (int i = tid; i < n_mel_tab; i += kWThreads) meta_s[i] = __ldg(meta + i);
-        }
-    }
-    __syncthreads();
-
-    float2 *xb = xall + warp * kWXchg;
-    float *magbuf = reinterpret_cast<float *>(xb); // [1025] magnitudes of the current frame (mel mode)
-    const float2 *win2 = reinterpret_cast<const float2 *>(win_s);
-
-    int cur = 0; // current track (frames are enumerated track after track)
-    float vmax = -INFINITY, vmin = INFINITY;
-    auto flush_range = [&](const StftTrack *td) {
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
-            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
-        }
-        if (lane == 0 && td->range_slot != nullptr && vmax >= vmin) {
-            atomicMax(td->range_slot, enc_ordered(vmax));
-            atomicMin(td->range_slot + 1, enc_ordered(vmin));
-        }
-        vmax = -INFINITY; vmin = INFINITY;
-    };
-
-    for (int g = blockIdx.x * kWWarps + warp; g < L.n_tiles; g += gridDim.x * kWWarps) {
-        // ---- which track / frame (tile_begin holds the frame prefix: one "tile" per frame) ----------------
-        int nxt = cur;
-        while (nxt + 1 < L.n_tracks && L.tracks[nxt + 1].tile_begin <= g) ++nxt;
-        if (nxt != cur) { flush_range(L.tracks + cur); cur = nxt; }
-        const StftTrack *__restrict__ td = L.tracks + cur;
-        const PcmView pv{td->pcm, td->n, td->ch, td->fmt, td->origin, td->avail};
-        const int t = g - td->tile_begin;
-        const long long S0 = (long long)(td->frame0 + t) * td->hop - td->win / 2 - td->pad_l; // global
-        const long long Sl = S0 - pv.origin;                                                  // local to the slice
-        float *__restrict__ out = td->out;
-        const int n_out = td->n_out;
-
-        float re[32][1], im[32][1];
-        // ---- A: windowed samples, z[32 m1 + lane] = (g[2m], g[2m+1]) ------------------------------------------
-        const bool interior = pv.ch == 1 && pv.fmt == PCM_F32 && S0 >= 0 && S0 + 2 * kWH <= pv.n && Sl >= 0 &&
-                              Sl + 2 * kWH <= pv.avail;
-        if (interior && ((Sl & 1) == 0) && ((reinterpret_cast<uintptr_t>(pv.pcm) & 7) == 0)) {
-            const float2 *__restrict__ p = reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(pv.pcm) + Sl) + lane;
-#pragma unroll
-            for (int m1 = 0; m1 < 32; ++m1) {
-                const float2 x = __ldg(p + 32 * m1);
-                const float2 w = win2[32 * m1 + lane];
-                re[m1][0] = x.x * w.x; im[m1][0] = x.y * w.y;
-            }
-        } else if (interior) {
-            const float *__restrict__ p = reinterpret_cast<const float *>(pv.pcm) + Sl + 2 * lane;
-#pragma unroll
-            for (int m1 = 0; m1 < 32; ++m1) {
-                const float2 w = win2[32 * m1 + lane];
-                re[m1][0] = __ldg(p + 64 * m1) * w.x; im[m1][0] = __ldg(p + 64 * m1 + 1) * w.y;
-            }
-        } else {
-#pragma unroll
-            for (int m1 = 0; m1 < 32; ++m1) {
-                const float2 w = win2[32 * m1 + lane];
-                const long long i = S0 + 64 * m1 + 2 * lane;
-                re[m1][0] = load_sample(pv, i) * w.x; im[m1][0] = load_sample(pv, i + 1) * w.y;
-            }
-        }
-        // ---- B: 32-point DFT over m1, twiddle W_1024^(lane k1) ----------------------------------------------------
-        dft_inplace<32, 0, 1, 32, 1>(re, im);
-#pragma unroll
-        for (int k1 = 1; k1 < 32; ++k1) {
-            const float2 w = tw2_s[k1 * 32 + lane];
-            const float xr = re[k1][0], xi = im[k1][0];
-            re[k1][0] = xr * w.x - xi * w.y; im[k1][0] = xr * w.y + xi * w.x;
-        }
-        // ---- C: transpose through the warp's buffer (pitch 33 float2: both sides conflict free) -----------------
-        __syncwarp(); // previous frame's magnitudes are consumed
-#pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) xb[k1 * 33 + lane] = make_float2(re[k1][0], im[k1][0]);
-        __syncwarp();
-#pragma unroll
-        for (int m2 = 0; m2 < 32; ++m2) { const float2 v = xb[lane * 33 + m2]; re[m2][0] = v.x; im[m2][0] = v.y; }
-        __syncwarp();
-        // ---- D: 32-point DFT over m2 -> Z[lane + 32 k2] in register k2 -----------------------------------------------
-        dft_inplace<32, 0, 1, 32, 1>(re, im);
-        // ---- E: real-FFT split (realfft.rs:140-157); partner bin lives in lane 32-lane, register 31-k2 ------------
-        const int pl = (32 - lane) & 31;
-        const bool l0 = lane == 0;
-        const size_t row = (size_t)t * (kWH + 1);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            // lane 0 pairs k = 32 j with 32 (32 - j): it offers register (32 - j) & 31 instead of 31 - j
-            const float sr = l0 ? re[(32 - j) & 31][0] : re[31 - j][0];
-            const float si = l0 ? im[(32 - j) & 31][0] : im[31 - j][0];
-            const float br = __shfl_sync(0xffffffffu, sr, pl), bi = __shfl_sync(0xffffffffu, si, pl);
-            const float ar = re[j][0], ai = im[j][0];
-            const int k = lane + 32 * j;
-            const float2 cs = spl_s[k]; // (cos, sin)(k pi / h)
-            const float sumr = ar + br, difr = ar - br, sumi = ai + bi, difi = ai - bi;
-            const float xr = 0.5f * (sumr + fmaf(cs.x, sumi, -cs.y * difr));
-            const float xi = 0.5f * (difi - fmaf(cs.y, sumi, cs.x * difr));
-            if (mode == MODE_COMPLEX) {
-                reinterpret_cast<float2 *>(out)[row + k] = make_float2(xr, xi);
-            } else {
-                const float mg = sqrt_approx(fmaf(xr, xr, xi * xi)); // lib.rs:124
-                if (mode == MODE_MEL_DB) magbuf[k] = mg;
-                else {
-                    float y = mg;
-                    if (mode == MODE_LIN_DB) { y = amp_to_db_dev(y); vmax = fmaxf(vmax, y); vmin = fminf(vmin, y); }
-                    out[row + k] = y;
-                }
-            }
-        }
-        if (l0) { // Nyquist bin: Z[0].re - Z[0].im (realfft.rs:157)
-            const float xr = re[0][0] - im[0][0];
-            if (mode == MODE_COMPLEX) reinterpret_cast<float2 *>(out)[row + kWH] = make_float2(xr, 0.0f);
-            else {
-                const float mg = fabsf(xr);
-                if (mode == MODE_MEL_DB) magbuf[kWH] = mg;
-                else {
-                    float y = mg;
-                    if (mode == MODE_LIN_DB) { y = amp_to_db_dev(y); vmax = fmaxf(vmax, y); vmin = fminf(vmin, y); }
-                    out[row + kWH] = y;
-                }
-            }
-        }
-        // ---- F: banded mel projection + dB (lanes <-> filters) --------------------------------------------------------
-        if (mode == MODE_MEL_DB) {
-            __syncwarp();
-            const int lg = td->mel_log2p, P = 1 << lg;
-            const int items = n_out << lg;
-            for (int w0 = 0; w0 < items; w0 += 32) {
-                const int wi = w0 + lane;
-                const int m = wi >> lg, plm = wi & (P - 1);
-                const bool valid = m < n_out;
-                int4 mt = make_int4(0, 0, 0, 0);
-                if (valid) mt = meta_s[m];
-                const int nj = mt.y > plm ? (mt.y - plm + P - 1) >> lg : 0;
-                const int njmax = __reduce_max_sync(0xffffffffu, nj);
-                const float *wp = wts_s + mt.z + plm;
-                const float *mp = magbuf + mt.x + plm;
-                float acc = 0.0f;
-                // loads are unconditional (the tables are zero-padded and the buffer is larger than the
-                // spectrum); taps past this lane's band are zeroed by the select
-                if (lg == 0) {
-#pragma unroll 4
-                    for (int jj = 0; jj < njmax; ++jj) acc = fmaf(mp[jj], jj < nj ? wp[jj] : 0.0f, acc);
-                } else {
-#pragma unroll 2
-                    for (int jj = 0; jj < njmax; ++jj) {
-                        const bool on = jj < nj;
-                        acc = fmaf(on ? mp[jj << lg] : 0.0f, on ? wp[jj << lg] : 0.0f, acc);
-                    }
-                }
-                for (int s = P >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-                if (valid && plm == 0) {
-                    const float y = amp_to_db_dev(acc);
-                    vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
-                    out[(size_t)t * n_out + m] = y;
-                }
-            }
-        }
-    }
-    if (mode == MODE_LIN_DB || mode == MODE_MEL_DB) flush_range(L.tracks + cur);
-}
-
+#if SGX_K1_PART <= 0
 // ---- small-F fallback: one CTA per frame, radix-2 Stockham, any power-of-two F >= 2 --------------------
 // Covers the reference's known-answer shapes (n_fft = 4, 256) and anything below the tuned sizes.
 __global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, int h)
@@ -1236,6 +849,8 @@ __global__ void __launch_bounds__(128) stft_generic_kernel(const StftLaunch L, i
     }
 }
 
+#endif // SGX_K1_PART <= 0
+
 int resident_sms()
 {
     int sms = 0, dev = 0;
@@ -1275,23 +890,62 @@ cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 // (16,2,4) 3.16 | (16,2,2) 3.38 -- sharing index math, twiddles and mel taps across V = 4 frames outweighs the
 // higher occupancy of the V = 2 variants and the fewer exchanges of radix 16.
 #ifdef SGX_K1_ALTERNATES // the other CTA shapes of the design-space measurements (make TUNE=-DSGX_K1_ALTERNATES)
-#define SGX_K1_ALT(X)   \
-    X(9, 8, 4, 8, 1)    \
-    X(10, 8, 4, 2, 2)   \
-    X(10, 8, 2, 2, 3)   \
-    X(10, 4, 4, 1, 4)   \
-    X(11, 8, 4, 1, 2)
+#define SGX_K1_ALT(X)      \
+    X(5, 9, 8, 4, 8, 1)    \
+    X(5, 10, 8, 4, 2, 2)   \
+    X(5, 10, 8, 2, 2, 3)   \
+    X(5, 10, 4, 4, 1, 4)   \
+    X(6, 10, 16, 2, 8, 1)  \
+    X(6, 11, 8, 4, 1, 2)
 #else
 #define SGX_K1_ALT(X)
 #endif
-#define SGX_K1_TABLE(X) \
-    X(8, 8, 4, 8, 2)    \
-    X(9, 8, 4, 4, 2)    \
-    X(10, 8, 4, 4, 1)   \
-    X(11, 8, 4, 2, 1)   \
-    X(12, 8, 4, 1, 1)   \
-    X(13, 8, 2, 1, 1)   \
+// (part, LOG2H, PTS, V, G, resident CTAs)
+#define SGX_K1_TABLE(X)    \
+    X(1, 8, 8, 4, 8, 2)    \
+    X(1, 9, 8, 4, 4, 2)    \
+    X(2, 10, 8, 4, 4, 1)   \
+    X(3, 11, 8, 4, 2, 1)   \
+    X(4, 12, 8, 4, 1, 1)   \
+    X(4, 13, 8, 2, 1, 1)   \
     SGX_K1_ALT(X)
+#define SGX_K1_NPARTS 6
+
+namespace {
+template <int PART>
+cudaError_t launch_rows(const StftConfig &cfg, const StftLaunch &L, size_t smem, cudaStream_t stream)
+{
+#define X(P, LG, PTS, V, G, MC)                                                                   \
+    if constexpr (PART < 0 || PART == P) {                                                        \
+        if (cfg.h == (1 << LG) && cfg.pts == PTS && cfg.vec == V && cfg.groups == G)              \
+            return launch_one<LG, PTS, V, G, MC>(L, smem, stream);                                \
+    }
+    SGX_K1_TABLE(X)
+#undef X
+    return cudaErrorInvalidValue; // not a row of this part
+}
+} // namespace
+
+#define SGX_K1_CAT2(a, b) a##b
+#define SGX_K1_CAT(a, b) SGX_K1_CAT2(a, b)
+#if SGX_K1_PART > 0
+cudaError_t SGX_K1_CAT(launch_stft_rows_, SGX_K1_PART)(const StftConfig &cfg, const StftLaunch &L, size_t smem, cudaStream_t stream)
+{
+    return launch_rows<SGX_K1_PART>(cfg, L, smem, stream);
+}
+#endif
+
+#if SGX_K1_PART <= 0
+#if SGX_K1_PART == 0
+cudaError_t launch_stft_rows_1(const StftConfig &, const StftLaunch &, size_t, cudaStream_t);
+cudaError_t launch_stft_rows_2(const StftConfig &, const StftLaunch &, size_t, cudaStream_t);
+cudaError_t launch_stft_rows_3(const StftConfig &, const StftLaunch &, size_t, cudaStream_t);
+cudaError_t launch_stft_rows_4(const StftConfig &, const StftLaunch &, size_t, cudaStream_t);
+#ifdef SGX_K1_ALTERNATES
+cudaError_t launch_stft_rows_5(const StftConfig &, const StftLaunch &, size_t, cudaStream_t);
+cudaError_t launch_stft_rows_6(const StftConfig &, const StftLaunch &, size_t, cudaStream_t);
+#endif
+#endif
 
 bool stft_config_for(size_t n_fft, StftConfig *cfg)
 {
@@ -1303,7 +957,7 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
     int want_pts = 0, want_v = 0, want_g = 0;
     if (const char *e = getenv("SGX_K1_VARIANT")) sscanf(e, "%d,%d,%d", &want_pts, &want_v, &want_g);
     bool chosen = false;
-#define X(LG, PTS, V, G, MC)                                                                     \
+#define X(P, LG, PTS, V, G, MC)                                                                  \
     if (h == (1 << LG)) {                                                                        \
         using TR = K1Traits<LG, PTS, V, G, MC>;                                                      \
         const bool match = want_pts == PTS && want_v == V && want_g == G;                        \
@@ -1318,34 +972,40 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
     }
     SGX_K1_TABLE(X)
 #undef X
-    // n_fft = 2048: SGX_K1W=1 selects the warp-per-frame kernel instead of the block kernel above.  Measured on
-    // B200 (C5): 65 % issue-slot use vs 51 %, but 1.25x the instructions (no sharing of index math, tables and
-    // mel taps across 4 frames) -> 9.9 ms vs 9.4 ms; kept as an evaluated alternative, off by default.
-    static const bool k1w_on = getenv("SGX_K1W") && atoi(getenv("SGX_K1W")) == 1;
-    cfg->warp_per_frame = false;
-    if (h == kWH && k1w_on && want_pts == 0) {
-        cfg->warp_per_frame = true; cfg->generic = false; cfg->fused = false;
-        cfg->pts = 32; cfg->vec = 1; cfg->groups = kWWarps; cfg->threads = kWThreads; cfg->min_ctas = 1;
-        cfg->fft_smem = 0;
-    }
+    // n_fft = 2048: the warp-per-frame-pair kernel is the default (SGX_K1W2=0 keeps the block kernel)
+    static const bool w2_off = getenv("SGX_K1W2") && atoi(getenv("SGX_K1W2")) == 0;
+    cfg->warp2 = h == 1024 && !cfg->generic && cfg->fused && !w2_off && want_pts == 0;
     return true;
 }
-
-size_t stft_warp_smem_bytes(int nnz, int n_mel) { return k1w_smem_bytes(nnz, n_mel); }
 
 size_t stft_max_dynamic_smem() { return 227 * 1024; }
 
 StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, int sample_floats)
 {
     StftTiling t{};
-    if (cfg.warp_per_frame) { // one "tile" per frame; nothing is staged per tile
-        t.frames_per_tile = 1; t.staged = 0; t.tile_floats = 0; t.smem_bytes = 0;
-        return t;
-    }
     if (cfg.generic) {
         t.frames_per_tile = 1; t.staged = 0; t.tile_floats = 0;
         t.smem_bytes = cfg.fft_smem;
         return t;
+    }
+    int want_nfr = 0;
+    if (const char *e = getenv("SGX_K1_NFR")) want_nfr = atoi(e);
+    if (cfg.warp2) {
+        // eight warps x two frames per round; the tile gets what the exchange planes, tables and filterbank leave
+        const size_t fixed = stft_warp2_fixed_smem(bank_floats);
+        const long cap_floats = stft_max_dynamic_smem() > fixed ? (long)((stft_max_dynamic_smem() - fixed) / sizeof(float)) : 0;
+        int best = 0;
+        for (int mult = 1; mult <= 4; ++mult) {
+            const int nfr = 16 * mult;
+            const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
+            if (need <= cap_floats && (nfr <= (want_nfr ? want_nfr : 32) || best == 0)) best = nfr;
+        }
+        if (best > 0) {
+            t.frames_per_tile = best; t.staged = 1; t.warp2 = 1; t.bank_floats = bank_floats; t.sample_floats = 1;
+            t.tile_floats = (int)((3 + (long)(best - 1) * max_hop + cfg.n_fft + 3) & ~3L) + 4;
+            t.smem_bytes = fixed + (size_t)t.tile_floats * sizeof(float);
+            return t;
+        }
     }
     const int unit = cfg.groups * cfg.vec;
     // per-CTA shared-memory budget for the register-limited number of resident CTAs (228 KB per SM,
@@ -1353,8 +1013,6 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, 
     const int ctas = cfg.min_ctas > 0 ? cfg.min_ctas : 1;
     size_t budget = (size_t)(228 * 1024) / ctas - 1024 - 512;
     if (budget > stft_max_dynamic_smem()) budget = stft_max_dynamic_smem();
-    int want_nfr = 0;
-    if (const char *e = getenv("SGX_K1_NFR")) want_nfr = atoi(e);
     static const bool no_bank = getenv("SGX_K1_NOBANK") && atoi(getenv("SGX_K1_NOBANK")) == 1;
     if (no_bank) bank_floats = 0;
     // First choice: the filterbank of a track gets its own region (loaded once per persistent CTA and
@@ -1386,20 +1044,6 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, 
     return t;
 }
 
-void make_warp_fft_tables(float2 *tw2 /*[32*32]*/, float2 *split_full /*[1024]*/)
-{
-    const double pi = 3.14159265358979323846264338327950288;
-    for (int k1 = 0; k1 < 32; ++k1)
-        for (int lane = 0; lane < 32; ++lane) {
-            const double a = -2.0 * pi * (double)(k1 * lane) / (double)kWH; // W_1024^(lane k1)
-            tw2[k1 * 32 + lane] = make_float2((float)cos(a), (float)sin(a));
-        }
-    for (int k = 0; k < kWH; ++k) {
-        const double a = pi * (double)k / (double)kWH;
-        split_full[k] = make_float2((float)cos(a), (float)sin(a));
-    }
-}
-
 void make_fft_tables(int h, float2 *tw, float2 *split)
 {
     const double pi = 3.14159265358979323846264338327950288;
@@ -1416,19 +1060,7 @@ void make_fft_tables(int h, float2 *tw, float2 *split)
 cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t stream)
 {
     if (L.n_tiles <= 0) return cudaSuccess;
-    if (cfg.warp_per_frame) {
-        const size_t smem = k1w_smem_bytes(L.mel_nnz, L.mel_rows);
-        cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(stft_warp_kernel), smem);
-        if (e != cudaSuccess) return e;
-        int sms = 0, dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-        const int grid = std::min(sms, (L.n_tiles + kWWarps - 1) / kWWarps);
-        stft_warp_kernel<<<grid, kWThreads, smem, stream>>>(L, L.mel_nnz, L.mel_rows);
-        count_launch();
-        return cudaGetLastError();
-    }
+    if (L.warp2) return launch_stft_warp2(L, stream);
     const size_t smem = cfg.generic ? cfg.fft_smem
                                     : 16 + (size_t)(L.tile_floats + L.bank_floats) * sizeof(float) + cfg.fft_smem;
     if (cfg.generic) {
@@ -1438,11 +1070,20 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t
         count_launch();
         return cudaGetLastError();
     }
-#define X(LG, PTS, V, G, MC) \
-    if (cfg.h == (1 << LG) && cfg.pts == PTS && cfg.vec == V && cfg.groups == G) return launch_one<LG, PTS, V, G, MC>(L, smem, stream);
-    SGX_K1_TABLE(X)
-#undef X
-    return cudaErrorInvalidValue;
+#if SGX_K1_PART < 0
+    return launch_rows<-1>(cfg, L, smem, stream);
+#else
+    cudaError_t e = launch_stft_rows_1(cfg, L, smem, stream);
+    if (e == cudaErrorInvalidValue) e = launch_stft_rows_2(cfg, L, smem, stream);
+    if (e == cudaErrorInvalidValue) e = launch_stft_rows_3(cfg, L, smem, stream);
+    if (e == cudaErrorInvalidValue) e = launch_stft_rows_4(cfg, L, smem, stream);
+#ifdef SGX_K1_ALTERNATES
+    if (e == cudaErrorInvalidValue) e = launch_stft_rows_5(cfg, L, smem, stream);
+    if (e == cudaErrorInvalidValue) e = launch_stft_rows_6(cfg, L, smem, stream);
+#endif
+    return e;
+#endif
 }
+#endif // SGX_K1_PART <= 0
 
 } // namespace sgx
