@@ -5,14 +5,16 @@
 
 A "step" is one pass of the hot path over one batch of synthetic PCM:
     MultiTrack.add_tracks (K1 fused analysis of every track -> dB, K2 global range incl. the
-    all-reduce across GPUs) followed by get_spec_image for every track (K3 -> RGBA, 100 px/s x 500).
+    all-reduce across GPUs, inside libsgx.so) followed by get_spec_image for every track (K3 -> RGBA, 100 px/s x 500).
 Default workload (`c5`, BASELINE.json configs[4], weak scaling): every GPU owns 32 synthetic
 10-minute 48 kHz mono tracks (256 tracks at 8 GPUs) analysed with the reference's MultiTrack defaults
 (W=1920, hop=480, n_fft=2048, default mel bank of 347 bands, 120 dB range).
 `value` times the step with PCM and pixels resident in HBM (CUDA events on the engine's stream, max over
 ranks); `e2e` times the same step through the host-buffer C ABI (pinned host PCM in, host RGBA out).
-`--impl reference` times the CPU restatement of the reference (oracle/) on the box's host cores.
-Prints ONE JSON line on rank 0.
+The default single-GPU run appends `configs`: the other BASELINE configs (C3 full, three points of the C4 sweep,
+C2, C1) measured in the same process, device-resident, compact.
+`--impl reference` times the CPU restatement of the reference (oracle/) on the box's host cores and imports
+nothing of the GPU package.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -31,6 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "audio-seconds/sec (spectrogram->RGBA)"
 UNIT = "audio-s/s"
 PX_PER_SEC, NHEIGHT = 100.0, 500  # benches/bench.rs:57
+FREQ_LINEAR, FREQ_MEL = 0, 1      # enum FreqScale, lib.rs:25-28 (== SGX_FREQ_*)
 
 
 def workload(name, n_fft=2048):
@@ -56,18 +59,13 @@ def workload(name, n_fft=2048):
                          "per-rate W/hop/n_fft of lib.rs:43-46, 128-band mel, dB + RGBA 100 px/s x 500")
     if name == "c4":  # one point of the long-window sweep; --n-fft picks F
         return dict(sr=44100, seconds=600, channels=1, tracks=1, seed=4004,
-                    settings=dict(win_length=n_fft, hop_length=n_fft // 4, n_fft=n_fft, freq_scale=0),
+                    settings=dict(win_length=n_fft, hop_length=n_fft // 4, n_fft=n_fft, freq_scale=FREQ_LINEAR),
                     desc=f"C4: 10 min x 44.1 kHz mono, n_fft=W={n_fft} hop={n_fft // 4} Hann, linear-frequency dB + RGBA 100 px/s x 500")
     if name == "c1":
         return dict(sr=48000, seconds=44.031854, channels=1, tracks=1, seed=1001,
-                    settings=dict(win_length=2048, hop_length=512, n_fft=2048, freq_scale=0),
+                    settings=dict(win_length=2048, hop_length=512, n_fft=2048, freq_scale=FREQ_LINEAR),
                     desc="C1: 48 kHz mono 44 s (N=2113529), n_fft=2048 hop=512 Hann, linear-frequency dB + RGBA 100 px/s x 500")
     raise SystemExit(f"unknown workload {name}")
-
-
-def alg_bytes_per_audio_second(sr, channels):
-    """f32 PCM read once + RGBA written once = 4*ch*sr + 100*500*4 bytes per audio second."""
-    return 4 * channels * sr + int(PX_PER_SEC) * NHEIGHT * 4
 
 
 class ClockSampler:
@@ -123,8 +121,17 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (a C restatement of the reference; no Rust toolchain exists to build the reference)
+# CPU arm: the oracle (a C restatement of the reference; no Rust toolchain exists to build the reference).
+# Nothing of the GPU package is imported here: parameters come from the oracle's own lib.rs:43-46 restatement.
 # ---------------------------------------------------------------------------------------------------------
+def cpu_params(orc, sr, settings):
+    win, hop, n_fft = orc.track_params(sr)
+    hop = settings.get("hop_length") or hop
+    win = settings.get("win_length") or (hop * 4 if settings.get("hop_length") else win)
+    n_fft = settings.get("n_fft") or (n_fft if not settings.get("win_length") else 1 << int(np.ceil(np.log2(win))))
+    return int(win), int(hop), int(n_fft)
+
+
 def cpu_sample(wl, cores):
     """A bounded sample of the workload: `cores` tracks (so the reference's per-track rayon parallelism,
     lib.rs:161-166, can use every core) of at most 120 s each."""
@@ -137,7 +144,7 @@ def cpu_sample(wl, cores):
         secs = min(int(wl["seconds"]), 60 if wl["channels"] == 2 else 44)
     base = synth.base_clip(secs * sr, sr, wl["seed"])
     wavs = [synth.derive_track(base, t) for t in range(ntr)]
-    if wl["channels"] == 2:  # the reference sums channels while loading (lib.rs:42); do it inside the timed call
+    if wl["channels"] == 2:  # the reference sums channels while loading (lib.rs:42)
         wavs = [w + np.roll(w, 1234) * np.float32(0.75) for w in wavs]
     return wavs, secs, ntr
 
@@ -145,30 +152,30 @@ def cpu_sample(wl, cores):
 def run_cpu(wl, steps, warmup):
     import oracle_binding
 
-    import msv_b200 as msv
-
     orc = oracle_binding.load()
     orc.set_num_threads(len(os.sched_getaffinity(0)))  # all host cores (torchrun pins OMP_NUM_THREADS=1)
     cores = orc.num_threads()
     wavs, secs, ntr = cpu_sample(wl, cores)
-    st = msv.Settings.default(**wl["settings"])
+    st = wl["settings"]
     sr = wl["sr"]
-    win, hop, n_fft = msv.track_params(sr, st)
-    mel = st.freq_scale == msv.FREQ_MEL
+    win, hop, n_fft = cpu_params(orc, sr, st)
+    mel = st.get("freq_scale", FREQ_MEL) == FREQ_MEL
     window = orc.calc_window(win, n_fft)
-    fb = None if not mel else (orc.calc_mel_fb(sr, n_fft, st.n_mel) if st.n_mel else orc.calc_mel_fb_default(sr, n_fft))
-    times = []
+    fb = None if not mel else (orc.calc_mel_fb(sr, n_fft, st["n_mel"]) if st.get("n_mel") else orc.calc_mel_fb_default(sr, n_fft))
+    times, imgs = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         # faithful variant: dense mel GEMM (lib.rs:131), FFT plan per frame in single-track mode (lib.rs:455);
-        # rendering runs across tracks on all threads (generous: display.rs is single-threaded per call)
-        orc.pipeline(wavs, [sr] * ntr, [(win, hop, n_fft)] * ntr, [window] * ntr, [fb] * ntr, mel_scale=mel,
-                     px_per_sec=PX_PER_SEC, nheight=NHEIGHT, channels=4, dense_mel=True, parallel_render=True)
+        # rendering runs across tracks on all threads (generous: display.rs is single-threaded per call);
+        # the output images are allocated once, by the first (warm-up) call
+        imgs, _, _ = orc.pipeline(wavs, [sr] * ntr, [(win, hop, n_fft)] * ntr, [window] * ntr, [fb] * ntr, mel_scale=mel,
+                                  px_per_sec=PX_PER_SEC, nheight=NHEIGHT, channels=4, dense_mel=True, parallel_render=True,
+                                  out_imgs=imgs)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec_per_step = float(np.median(times)) if times else float("nan")
     return {"value": ntr * secs / sec_per_step, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{ntr} tracks x {secs} s of the same synthetic workload per step, median of {len(times)} steps; "
+            "sample": f"{ntr} tracks x {secs} s of the same synthetic workload per step, median of {len(times)} steps after {warmup} warm-up; "
                       "C restatement of the reference (oracle/, gcc -O3, OpenMP across tracks like rayon); "
                       "the Rust reference itself cannot be built here (no cargo/rustc)",
             "ms_per_step": sec_per_step * 1e3}
@@ -177,32 +184,20 @@ def run_cpu(wl, steps, warmup):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
-def run_gpu(args, wl, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-
-    import msv_b200 as msv
-    import synth
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+def make_batch(wl, rank, world, dev, torch, synth):
+    """Synthetic batch derived on the device from one uploaded base clip.  Returns
+    (global ids, device tensors, samples per track, rates, channels)."""
     sr, ch, ntr = wl["sr"], wl["channels"], wl["tracks"]
     n = int(round(wl["seconds"] * sr)) if wl["seconds"] != 44.031854 else 2113529
-    st = msv.Settings.default(**wl["settings"])
-
-    # ---- synthetic batch, derived on the device from one uploaded base clip ----
-    gids = [rank + i * world for i in range(ntr)]  # track t -> GPU t mod G
+    gids = [rank + i * world for i in range(ntr)]  # track t -> GPU t mod G: what the library's sharding keeps on this rank
     tracks = []
-    if wl.get("sliced"):
-        return run_gpu_sliced(args, wl, rank, world, local_rank, st, n, sr, ch, dev)
     if "srs" in wl:  # mixed sample rates: one clip per rate (every GPU holds the same six tracks)
         srs = list(wl["srs"])
         ns = [int(round(wl["seconds"] * r)) for r in srs]
         for i, (r, m) in enumerate(zip(srs, ns)):
             tracks.append(torch.from_numpy(synth.derive_track(synth.base_clip(m, r, wl["seed"] + r), i)).to(dev))
     else:
-        base_h = synth.base_clip(n, sr, wl["seed"])
-        base = torch.from_numpy(base_h).to(dev)
+        base = torch.from_numpy(synth.base_clip(n, sr, wl["seed"])).to(dev)
         for t in gids:
             gain, shift = synth.track_gain_shift(t, n)
             x = torch.roll(base, -shift) * float(gain)
@@ -210,206 +205,176 @@ def run_gpu(args, wl, rank, world, local_rank):
                 x = torch.stack([x, torch.roll(x, 1234) * 0.75], dim=1).contiguous()
             tracks.append(x)
         del base
-        ns = [n] * ntr
-        srs = [sr] * ntr
-    sm = msv.ShardedMultiTrack(st, device=local_rank)
+        ns, srs = [n] * ntr, [sr] * ntr
+    return gids, tracks, ns, srs, [ch] * ntr
+
+
+def measure_device(msv, torch, dist, wl, st, rank, world, local_rank, steps, warmup, clocks=True):
+    """`value`: the step with PCM and pixels resident in HBM.  Returns a dict (rank 0) or None."""
+    import synth
+
+    dev = torch.device("cuda", local_rank)
+    gids, tracks, ns, srs, chs = make_batch(wl, rank, world, dev, torch, synth)
+    ntr, ch = len(gids), wl["channels"]
+    sm = msv.ShardedMultiTrack(st, device=local_rank)   # attaches the library's NCCL communicator when world > 1
     sm.mt.set_profiling(True)
-    ids = list(range(ntr))
+    sm.mt.set_global_max_sr(max(srs))                    # known up front: keeps the step free of host synchronisation
     ptrs = [x.data_ptr() for x in tracks]
-    chs = [ch] * ntr
     nwidths = [int(np.float32(PX_PER_SEC) * np.float32(m) / np.float32(r)) for m, r in zip(ns, srs)]
     caps = [w * NHEIGHT * 4 for w in nwidths]
-    img_bytes = caps[0]
     outs = [torch.empty(c, dtype=torch.uint8, device=dev) for c in caps]
     optrs = [o.data_ptr() for o in outs]
 
     def step():
-        sm.add_tracks_device(ids, ptrs, ns, srs, chs, exchange_max_sr=False)
-        sm.render_device(ids, PX_PER_SEC, NHEIGHT, 4, optrs, caps)
+        sm.add_tracks_device(gids, ptrs, ns, srs, chs)
+        sm.render_device(gids, PX_PER_SEC, NHEIGHT, 4, optrs, caps)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sm.mt.set_global_max_sr(max(srs))
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and clocks:
+        sampler.start()
     l0 = msv.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k1_ms, k3_ms = [], []
     barrier()
     ev0.record(sm.stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     ev1.record(sm.stream)
     barrier()
     launches = msv.kernel_launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = sampler.stop() if (rank == 0 and clocks) else None
     ms_total = ev0.elapsed_time(ev1)
-    # per-kernel durations (CUDA events on the engine's stream around K1 / K3), a few extra steps
-    for _ in range(3):
-        for _ in range(3):  # back-to-back steps: the events of the last one are read in steady state
+    k1_ms, k3_ms = [], []
+    for _ in range(3):  # per-kernel durations (CUDA events on the engine's stream around K1 / K3), steady state
+        for _ in range(3):
             step()
         a, r = sm.mt.stage_times()
         k1_ms.append(a); k3_ms.append(r)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = float(t.item()) / steps
     audio_s_per_gpu = float(sum(m / r for m, r in zip(ns, srs)))
-    value = audio_s_per_gpu * world / (ms_step * 1e-3)
-
-    # ---- e2e: the host-buffer C ABI (pinned host PCM -> add_tracks_pcm -> get_spec_image_rgba -> host) ----
-    e2e = None
-    if not args.no_e2e and "srs" not in wl:
-        e2e_tracks = ntr
-        host_in = [torch.empty(x.shape, dtype=torch.float32).pin_memory() for x in tracks[:e2e_tracks]]
-        for h, x in zip(host_in, tracks):
-            h.copy_(x)
-        host_out = [torch.empty(img_bytes, dtype=torch.uint8).pin_memory() for _ in range(e2e_tracks)]
-        np_in = [h.numpy() for h in host_in]
-        mt2 = msv.MultiTrack(st, device=local_rank)
-        import ctypes as C
-
-        def e2e_step():
-            mt2.add_tracks_pcm(list(range(e2e_tracks)), np_in, srs[:e2e_tracks])
-            for i in range(e2e_tracks):
-                need = C.c_size_t()
-                msv._check(msv._lib.sgx_mt_get_spec_image_rgba(mt2._h, i, PX_PER_SEC, NHEIGHT, host_out[i].data_ptr(), img_bytes, C.byref(need)))
-
-        e2e_step()
-        barrier()
-        reps = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            e2e_step()
-        torch.cuda.synchronize(dev)
-        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": e2e_tracks * n / sr * world / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host_in)),
-               "d2h_bytes_per_step": int(img_bytes * e2e_tracks), "ms_per_step": float(dt.item()) * 1e3,
-               "api": "sgx_mt_add_tracks_pcm (f32 host PCM) + sgx_mt_get_spec_image_rgba per track, pinned host buffers"}
-        # Two batches in flight: a second handle (own stream, own output buffers) runs the same steps on a second
-        # host thread, half a step out of phase.  Inside ONE step the global dB range forces upload -> analysis ->
-        # render -> download in sequence, so a single handle uses one PCIe direction at a time; two handles let the
-        # upload of one batch run under the download of the other.  Reported next to the headline, not instead of it.
-        if not args.no_e2e2 and world == 1:  # one rank only: it pins a second set of output buffers on the host
-            import threading
-            mt3 = msv.MultiTrack(st, device=local_rank)
-            host_out2 = [torch.empty(img_bytes, dtype=torch.uint8).pin_memory() for _ in range(e2e_tracks)]
-
-            def steps_on(mt, outs, count, delay):
-                time.sleep(delay)
-                for _ in range(count):
-                    mt.add_tracks_pcm(list(range(e2e_tracks)), np_in, srs[:e2e_tracks])
-                    for i in range(e2e_tracks):
-                        need = C.c_size_t()
-                        msv._check(msv._lib.sgx_mt_get_spec_image_rgba(mt._h, i, PX_PER_SEC, NHEIGHT, outs[i].data_ptr(), img_bytes, C.byref(need)))
-
-            steps_on(mt3, host_out2, 1, 0.0)  # warm-up of the second handle
-            torch.cuda.synchronize(dev)
-            barrier()
-            reps2 = max(2, reps)
-            step_s = float(dt.item())
-            th = [threading.Thread(target=steps_on, args=(mt2, host_out, reps2, 0.0)),
-                  threading.Thread(target=steps_on, args=(mt3, host_out2, reps2, 0.5 * step_s))]
-            t0 = time.perf_counter()
-            for t_ in th: t_.start()
-            for t_ in th: t_.join()
-            torch.cuda.synchronize(dev)
-            dt2 = torch.tensor([(time.perf_counter() - t0) / (2 * reps2)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
-            same = bool(torch.equal(host_out[0], host_out2[0]) and torch.equal(host_out[-1], host_out2[-1]))
-            e2e["two_batches_in_flight"] = {"value": e2e_tracks * n / sr * world / float(dt2.item()), "ms_per_step": float(dt2.item()) * 1e3,
-                                            "steps": 2 * reps2, "outputs_identical": same,
-                                            "note": "two MultiTrack handles on two host threads, half a step out of phase: upload of one batch under the download of the other"}
-            mt3.close()
-            del host_out2
-        # the same batch shape with 16-bit host PCM (what the WAV fixtures hold; sgx_mt_add_tracks_pcm_i16)
-        del host_in, np_in
-        base16 = torch.from_numpy(synth.base_clip_i16(n, sr, wl["seed"]))
-        host16 = []
-        for t in gids[:e2e_tracks]:
-            x = torch.roll(base16, -synth.track_gain_shift(t, n)[1])
-            if ch == 2:
-                x = torch.stack([x, torch.roll(x, 1234)], dim=1).contiguous()
-            host16.append(x.pin_memory())
-        np16 = [h.numpy() for h in host16]
-
-        def e2e16_step():
-            mt2.add_tracks_pcm(list(range(e2e_tracks)), np16, srs[:e2e_tracks])
-            for i in range(e2e_tracks):
-                need = C.c_size_t()
-                msv._check(msv._lib.sgx_mt_get_spec_image_rgba(mt2._h, i, PX_PER_SEC, NHEIGHT, host_out[i].data_ptr(), img_bytes, C.byref(need)))
-
-        e2e16_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            e2e16_step()
-        torch.cuda.synchronize(dev)
-        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e["int16_pcm"] = {"value": e2e_tracks * n / sr * world / float(dt.item()), "ms_per_step": float(dt.item()) * 1e3,
-                            "h2d_bytes_per_step": int(sum(h.numel() * 2 for h in host16)),
-                            "api": "sgx_mt_add_tracks_pcm_i16 (int16 host PCM, scaled on the GPU) + sgx_mt_get_spec_image_rgba"}
-        mt2.close()
-
-    # parity spot check of what was timed (smoke-level; the real gate is tests/ -m gpu)
     sm.synchronize()
     rng = (sm.get_max_db(), sm.get_min_db())
-    shapes = {i: sm.mt.spec_shape(i) for i in ids}
+    shapes = {i: sm.mt.spec_shape(i) for i in gids}
     sm.close()
+    res = {"tracks": tracks, "gids": gids, "ns": ns, "srs": srs, "chs": chs, "caps": caps}
     if rank != 0:
-        return None
+        return res
     peak, peak_src = measured_peak()
     alg_step = float(sum(4 * ch * m + c for m, c in zip(ns, caps)))  # per GPU per step: PCM in + RGBA out
-    k1 = float(np.median(k1_ms)); k3 = float(np.median(k3_ms))
-    db_bytes = 0
-    for i in ids:
-        T_i, n_out_i = shapes[i]
-        db_bytes += 4 * T_i * n_out_i
-    k1_own = float(sum(4 * ch * m for m in ns) + db_bytes)   # PCM read + dB written
-    k3_own = float(db_bytes + sum(caps))                      # dB read + pixels written
-    traffic = None
-    try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            tr = json.load(f).get(args.workload)
-        if tr and not (args.tracks or args.seconds):
-            traffic = tr["k1_stft_db_bytes"] / tr["audio_seconds_in_capture"] * audio_s_per_gpu
-    except Exception:
-        traffic = None
-    roofline = {"bound": "hbm", "kernel": "stft_db_kernel (K1, fused frame/window/rFFT/|X|/mel/dB)",
-                "achieved": alg_step / (k1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_step / (k1 * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_step, "kernel_ms": k1,
-                "note": "algorithmic bytes = SURVEY 8(d) per-unit figure (f32 PCM in + RGBA out) x audio seconds per launch"}
-    step_roof = {"achieved": alg_step / (ms_step * 1e-3) / 1e9, "frac": alg_step / (ms_step * 1e-3) / 1e9 / peak,
-                 "k1_ms": k1, "k3_ms": k3, "step_ms": ms_step, "k1_ms_samples": k1_ms, "k3_ms_samples": k3_ms,
-                 "k1_own_bytes_gbs": k1_own / (k1 * 1e-3) / 1e9, "k3_own_bytes_gbs": k3_own / (k3 * 1e-3) / 1e9,
-                 "note": "whole step (K1+K2+K3) against the same algorithmic bytes; *_own_bytes = each kernel's own minimal HBM traffic incl. the dB intermediate"}
-    return {"value": value, "ms_per_step": ms_step, "roofline": roofline, "roofline_step": step_roof, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clk, "db_range": rng}
+    k1, k3 = float(np.median(k1_ms)), float(np.median(k3_ms))
+    db_bytes = sum(4 * shapes[i][0] * shapes[i][1] for i in gids)
+    res.update({
+        "value": audio_s_per_gpu * world / (ms_step * 1e-3), "ms_per_step": ms_step, "launches": int(launches), "clocks": clk,
+        "db_range": rng, "k1_ms": k1, "k3_ms": k3, "k1_ms_samples": k1_ms, "k3_ms_samples": k3_ms, "alg_step": alg_step,
+        "k1_own": float(sum(4 * ch * m for m in ns) + db_bytes), "k3_own": float(db_bytes + sum(caps)),
+        "audio_s_per_gpu": audio_s_per_gpu, "peak": peak, "peak_src": peak_src})
+    return res
 
 
-def run_gpu_sliced(args, wl, rank, world, local_rank, st, n, sr, ch, dev):
-    """One track, time-sharded: rank r owns the columns [nw*r/G, nw*(r+1)/G) (sgx_slice_plan)."""
-    import torch
-    import torch.distributed as dist
-
-    import msv_b200 as msv
+def measure_e2e(msv, torch, dist, wl, st, rank, world, local_rank, batch, steps):
+    """The same step through the host-buffer C ABI: pinned host PCM -> sgx_mt_add_tracks_pcm -> sgx_mt_get_spec_images
+    (batched, renders and downloads pipelined inside the library) -> pinned host RGBA."""
     import synth
 
+    dev = torch.device("cuda", local_rank)
+    tracks, gids, ns, srs, caps = batch["tracks"], batch["gids"], batch["ns"], batch["srs"], batch["caps"]
+    ntr, ch, n, sr = len(gids), wl["channels"], batch["ns"][0], wl["sr"]
+    host_in = [torch.empty(x.shape, dtype=torch.float32).pin_memory() for x in tracks]
+    for h, x in zip(host_in, tracks):
+        h.copy_(x)
+    np_in = [h.numpy() for h in host_in]
+    outs = [[torch.empty(c, dtype=torch.uint8).pin_memory() for c in caps] for _ in range(2)]
+    mt = msv.MultiTrack(st, device=local_rank)
+    if world > 1:
+        mt.attach_nccl(msv.sharded.broadcast_unique_id(device=f"cuda:{local_rank}"), rank, world)
+    audio_s = float(sum(m / r for m, r in zip(ns, srs)))
+    h2d = int(sum(h.numel() * 4 for h in host_in)); d2h = int(sum(caps))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, reps):
+        fn(0)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(reps):
+            fn(k + 1)
+        mt.wait_images()
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        per_rank = [float(dt.item())]
+        if world > 1:
+            parts = [torch.zeros_like(dt) for _ in range(world)]
+            dist.all_gather(parts, dt)
+            per_rank = [float(p.item()) for p in parts]
+        return max(per_rank), per_rank
+
+    reps = max(2, min(steps, 4))
+
+    def sync_step(k):   # one batch at a time: upload, analyse, render, download, done
+        mt.add_tracks_pcm(gids, np_in, srs)
+        mt.get_spec_images(gids, PX_PER_SEC, NHEIGHT, 4, out=outs[0])
+
+    dt, mine = timed(sync_step, reps)
+    gbs = lambda nbytes, secs: [round(nbytes / t / 1e9, 2) for t in secs]  # achieved link rate of every rank over its own step
+    e2e = {"value": audio_s * world / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
+           "api": "sgx_mt_add_tracks_pcm (f32 host PCM) + sgx_mt_get_spec_images (batched host RGBA; renders and downloads "
+                  "pipelined inside libsgx.so), pinned host buffers, one batch at a time",
+           "per_rank_link_gbs": {"h2d_plus_d2h_over_step": gbs(h2d + d2h, mine)}}
+
+    def piped_step(k):  # the downloads of batch k run under the upload + analysis of batch k+1 (one handle)
+        mt.add_tracks_pcm(gids, np_in, srs)
+        mt.get_spec_images(gids, PX_PER_SEC, NHEIGHT, 4, out=outs[k & 1], wait=False)
+
+    dtp, minep = timed(piped_step, reps + 1)
+    same = bool(torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][-1], outs[1][-1]))
+    e2e["pipelined"] = {"value": audio_s * world / dtp, "ms_per_step": dtp * 1e3, "outputs_identical": same,
+                        "per_rank_link_gbs": {"h2d": gbs(h2d, minep), "d2h": gbs(d2h, minep)},
+                        "api": "the same calls with sgx_mt_get_spec_images_async: the next add_tracks is issued while the images of "
+                               "this batch are still on the wire (uploads and downloads overlap; two sets of host output buffers)"}
+    # the same batch shape with 16-bit host PCM (what WAV files hold and add_tracks(paths) uploads; sgx_mt_add_tracks_pcm_i16)
+    del host_in, np_in
+    base16 = torch.from_numpy(synth.base_clip_i16(n, sr, wl["seed"]))
+    host16 = []
+    for t in gids:
+        x = torch.roll(base16, -synth.track_gain_shift(t, n)[1])
+        if ch == 2:
+            x = torch.stack([x, torch.roll(x, 1234)], dim=1).contiguous()
+        host16.append(x.pin_memory())
+    np16 = [h.numpy() for h in host16]
+    h2d16 = int(sum(h.numel() * 2 for h in host16))
+
+    def i16_step(k):
+        mt.add_tracks_pcm(gids, np16, srs)
+        mt.get_spec_images(gids, PX_PER_SEC, NHEIGHT, 4, out=outs[k & 1], wait=False)
+
+    dt16, mine16 = timed(i16_step, reps + 1)
+    e2e["int16_pcm_pipelined"] = {"value": audio_s * world / dt16, "ms_per_step": dt16 * 1e3, "h2d_bytes_per_step": h2d16,
+                                  "per_rank_link_gbs": {"h2d": gbs(h2d16, mine16), "d2h": gbs(d2h, mine16)},
+                                  "api": "sgx_mt_add_tracks_pcm_i16 (int16 host PCM, scaled on the GPU) + sgx_mt_get_spec_images_async"}
+    mt.close()
+    return e2e
+
+
+def run_gpu_sliced(args, wl, rank, world, local_rank, st, msv, torch, dist):
+    """One track, time-sharded: rank r owns the columns [nw*r/G, nw*(r+1)/G) (sgx_slice_plan)."""
+    import synth
+
+    dev = torch.device("cuda", local_rank)
+    sr, ch = wl["sr"], wl["channels"]
+    n = int(round(wl["seconds"] * sr))
     base = synth.base_clip(n, sr, wl["seed"])
     nw = msv.calc_nwidth_like(PX_PER_SEC, n, sr)
     ob = nw * rank // world
@@ -427,10 +392,9 @@ def run_gpu_sliced(args, wl, rank, world, local_rank, st, n, sr, ch, dev):
 
     def step():
         sm.stream.wait_stream(torch.cuda.current_stream(dev))
-        sm.mt.add_track_slice_device(0, x.data_ptr(), sb, sc, n, sr, ch, fb, fc)
-        with torch.cuda.stream(sm.stream):
-            msv.sharded.all_reduce_range(sm._range, sm.group)
-        sm.mt.commit_range_device()
+        sm.mt.add_track_slice_device(0, x.data_ptr(), sb, sc, n, sr, ch, fb, fc)  # the range exchange happens inside
+        if world == 1:
+            sm.mt.commit_range_device()
         sm.mt.render_slice_device(0, PX_PER_SEC, NHEIGHT, 4, ob, oc, out.data_ptr(), out.numel())
 
     def barrier():
@@ -482,6 +446,50 @@ def run_gpu_sliced(args, wl, rank, world, local_rank, st, n, sr, ch, dev):
             "gpu_launches": int(launches), "clocks": clk, "db_range": rng, "scaling": "strong"}
 
 
+def roofline_of(args, d, workload_name):
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get(workload_name)
+        if tr and not (args.tracks or args.seconds):
+            traffic = tr["k1_stft_db_bytes"] / tr["audio_seconds_in_capture"] * d["audio_s_per_gpu"]
+    except Exception:
+        traffic = None
+    k1, k3, alg, peak = d["k1_ms"], d["k3_ms"], d["alg_step"], d["peak"]
+    roofline = {"bound": "hbm", "kernel": "stft_db_kernel (K1, fused frame/window/rFFT/|X|/mel/dB)",
+                "achieved": alg / (k1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg / (k1 * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": d["peak_src"],
+                "algorithmic_bytes_per_launch": alg, "kernel_ms": k1,
+                "note": "algorithmic bytes = SURVEY 8(d) per-unit figure (f32 PCM in + RGBA out) x audio seconds per launch"}
+    step = {"achieved": alg / (d["ms_per_step"] * 1e-3) / 1e9, "frac": alg / (d["ms_per_step"] * 1e-3) / 1e9 / peak,
+            "k1_ms": k1, "k3_ms": k3, "step_ms": d["ms_per_step"], "k1_ms_samples": d["k1_ms_samples"], "k3_ms_samples": d["k3_ms_samples"],
+            "k1_own_bytes_gbs": d["k1_own"] / (k1 * 1e-3) / 1e9, "k3_own_bytes_gbs": d["k3_own"] / (k3 * 1e-3) / 1e9,
+            "note": "whole step (K1+K2+K3) against the same algorithmic bytes; *_own_bytes = each kernel's own minimal HBM traffic incl. the dB intermediate"}
+    return roofline, step
+
+
+def other_configs(msv, torch, dist, args):
+    """BASELINE.json configs 0-3 next to the headline, device-resident, one GPU, compact."""
+    out = []
+    plan = [("c3", 2048, 0), ("c4", 512, 4), ("c4", 2048, 4), ("c4", 16384, 4), ("c2", 2048, 0), ("c1", 2048, 0)]
+    for name, n_fft, tracks in plan:
+        wl = workload(name, n_fft)
+        if tracks:
+            wl["tracks"] = tracks  # the C4 config is ONE 10-minute track per FFT size; four are batched so the persistent grid is filled
+        st = msv.Settings.default(**wl["settings"])
+        try:
+            d = measure_device(msv, torch, dist, wl, st, 0, 1, 0, steps=5, warmup=3, clocks=False)
+            out.append({"workload": name + (f"_{n_fft}" if name == "c4" else ""), "tracks": wl["tracks"], "value": d["value"],
+                        "ms_per_step": d["ms_per_step"], "k1_ms": d["k1_ms"], "k3_ms": d["k3_ms"],
+                        "frac_k1": d["alg_step"] / (d["k1_ms"] * 1e-3) / 1e9 / d["peak"],
+                        "frac_step": d["alg_step"] / (d["ms_per_step"] * 1e-3) / 1e9 / d["peak"], "gpu_launches_per_step": d["launches"] / 5,
+                        "db_range": d["db_range"]})
+        except Exception as ex:  # a secondary config must not take the headline down
+            out.append({"workload": name, "error": str(ex)[:200]})
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -494,8 +502,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=0, help="override track length (profiling runs only)")
     ap.add_argument("--channels", type=int, default=0, help="override the channel count of the workload (experiments only)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-e2e2", action="store_true", help="skip the two-batches-in-flight variant of the e2e measurement")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the compact C1-C4 entries of the default run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -511,15 +519,15 @@ def main():
     cfg = {"workload": wl["desc"], "px_per_sec": PX_PER_SEC, "nheight": NHEIGHT,
            "l2": "inputs larger than L2: every step streams the whole PCM batch and writes every pixel (GBs per step vs 126 MB L2)"
                  if args.workload != "c1" else "C1 fits in L2; not a headline number",
-           "sharding": "track t -> GPU t mod G; one 8-byte all-reduce(MAX) of {max,-min} per step"}
+           "sharding": "track t -> GPU t mod G inside libsgx.so; one 16-byte ncclAllReduce(MAX) of {max,-min,max_sr,max_sec} per step on the engine's stream"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 5))
-        cb = run_cpu(wl, steps, max(1, min(args.warmup, 1)))
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        cb = run_cpu(wl, steps, warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-                "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -528,12 +536,33 @@ def main():
     import torch
     import torch.distributed as dist
 
+    import msv_b200 as msv
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
     if world > 1:
-        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    res = run_gpu(args, wl, rank, world, local_rank)
+    st = msv.Settings.default(**wl["settings"])
+    if wl.get("sliced"):
+        res = run_gpu_sliced(args, wl, rank, world, local_rank, st, msv, torch, dist)
+        roofline, step_roof = (res["roofline"], res["roofline_step"]) if res else (None, None)
+        e2e, extra = None, None
+    else:
+        d = measure_device(msv, torch, dist, wl, st, rank, world, local_rank, args.steps, args.warmup)
+        e2e = None
+        if not args.no_e2e and "srs" not in wl:
+            e2e = measure_e2e(msv, torch, dist, wl, st, rank, world, local_rank, d, args.steps)
+        res = None
+        if rank == 0:
+            roofline, step_roof = roofline_of(args, d, args.workload)
+            res = {"value": d["value"], "ms_per_step": d["ms_per_step"], "gpu_launches": d["launches"], "clocks": d["clocks"],
+                   "db_range": d["db_range"]}
+        del d
+        torch.cuda.empty_cache()
+        extra = None
+        if rank == 0 and world == 1 and args.workload == "c5" and not args.no_configs and not (args.tracks or args.seconds):
+            extra = other_configs(msv, torch, dist, args)
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu and not wl.get("sliced"):
         cb = run_cpu(wl, 3, 1)
@@ -544,9 +573,11 @@ def main():
         return 0
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": cfg, "roofline": res["roofline"], "roofline_step": res["roofline_step"],
-            "cpu_baseline": cb, "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
+            "data": "synthetic", "config": cfg, "roofline": roofline, "roofline_step": step_roof,
+            "cpu_baseline": cb, "e2e": e2e, "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
             "db_range": res["db_range"]}
+    if extra is not None:
+        line["configs"] = extra
     print(json.dumps(line))
     return 0
 

@@ -17,8 +17,9 @@
  *     out == NULL only reports the required size.
  *   - "host" pointers are ordinary CPU memory; "_device" variants take CUDA device pointers of
  *     the handle's device and enqueue work on the handle's stream without synchronising.
- *   - a handle is bound to one CUDA device and one stream and is not thread-safe (the reference's
- *     mutators take `&mut self`).  Multi-GPU drivers own one handle per device.
+ *   - a handle is not thread-safe (the reference's mutators take `&mut self`).  sgx_mt_new / _ex bind it to
+ *     one CUDA device and one stream; sgx_mt_new_sharded spreads the tracks of ONE handle over several
+ *     devices of this process; sgx_mt_attach_nccl joins the handles of several processes (one per GPU).
  *   - there is no CPU fallback: if no CUDA device is usable the constructors fail with
  *     SGX_ERR_CUDA.
  */
@@ -49,7 +50,8 @@ enum {
     SGX_ERR_CUDA = 4,       /* CUDA runtime / no device / kernel image missing                    */
     SGX_ERR_STATE = 5,      /* call order (e.g. image requested before any track exists)          */
     SGX_ERR_NOMEM = 6,
-    SGX_ERR_BUFFER = 7      /* caller buffer too small; *written holds the required size          */
+    SGX_ERR_BUFFER = 7,     /* caller buffer too small; *written holds the required size          */
+    SGX_ERR_NCCL = 8        /* libnccl.so.2 missing or a collective failed                         */
 };
 
 /* Message of the last error raised on this thread ("" if none).  Never NULL. */
@@ -97,6 +99,30 @@ SGX_API int sgx_mt_new(sgx_multitrack **out);
 SGX_API int sgx_mt_new_ex(const sgx_settings *settings, int device, void *cuda_stream,
                           sgx_multitrack **out);
 SGX_API void sgx_mt_free(sgx_multitrack *mt);
+
+/* --- multi-GPU inside the library -------------------------------------------------------------
+ * The reference parallelises add_tracks over tracks (rayon, lib.rs:161-166) and reduces the dB range over all
+ * of them (lib.rs:194-209).  Here track id t lives on shard t mod G; PCM, dB and pixels never leave their GPU;
+ * the one exchange of the path -- {max, -min, max_sr, max_sec}, 16 bytes, all-reduce(MAX) -- is an
+ * ncclAllReduce enqueued by the library on the stream that carries the analysis and the render, between the
+ * two: no host round trip.  NCCL is loaded at run time (dlopen of libnccl.so.2): libsgx.so links without it
+ * and only these entry points can return SGX_ERR_NCCL.
+ *
+ * One process, several GPUs: a handle with one engine per listed device (devices == NULL or n_devices == 0: every
+ * visible device).  Every call of surface 1 works on it unchanged: ids route to their device, device-pointer
+ * arguments of track t must live on device devices[t mod G], time slices (n3) need single-device handles. */
+SGX_API int sgx_mt_new_sharded(const sgx_settings *settings, const int *devices, size_t n_devices,
+                               sgx_multitrack **out);
+/* One process per GPU (torchrun / MPI style): rank 0 draws an id, ships the 128 bytes to every rank by any host
+ * channel, and every rank attaches its own single-device handle (a collective call).  From then on the handle is
+ * one shard of a global MultiTrack: sgx_mt_add_tracks* take the WHOLE id list on every rank and keep the tracks
+ * with id mod world == rank (entries of other ranks may carry NULL pointers; a rank only opens its own files),
+ * sgx_mt_remove_track must be called on every rank, and get_max_db / get_min_db / get_max_sec / image geometry
+ * reflect all ranks.  Per-track calls answer for owned ids only (SGX_ERR_UNKNOWN_ID otherwise). */
+SGX_API int sgx_nccl_unique_id(uint8_t out[128]);
+SGX_API int sgx_mt_attach_nccl(sgx_multitrack *mt, const uint8_t unique_id[128], int rank, int world);
+/* engines inside the handle; rank / world of an attached single-device handle (0 / 1 otherwise) */
+SGX_API int sgx_mt_get_device_count(sgx_multitrack *mt, int *n_devices, int *rank, int *world);
 
 /* MultiTrack::add_tracks(&mut self, id_list: &[usize], path_list: &str) -> Result<bool, JsValue>
  * lib.rs:171-191.  path_list is '\n'-joined (lib.rs:173).  *changed receives the returned bool
@@ -149,6 +175,23 @@ SGX_API int sgx_mt_get_spec_images_device(sgx_multitrack *mt, const size_t *id_l
                                           uint8_t *const *d_out, const size_t *cap,
                                           size_t *written);
 
+/* Host-buffer form of the batched call: what a viewer does after add_tracks -- get_spec_image for every track
+ * (lib.rs:294-298; the bench loop of benches/bench.rs:47-60 over a list of ids).  All renders are enqueued at
+ * once into per-image device staging and the device->host copies run on a second stream underneath them; one
+ * synchronisation at the end.  out[i] == NULL skips an image, out == NULL only reports sizes.  Pinned (page-locked)
+ * host buffers make the copies truly asynchronous. */
+SGX_API int sgx_mt_get_spec_images(sgx_multitrack *mt, const size_t *id_list, size_t n_ids,
+                                   float px_per_sec, uint32_t nheight, int channels,
+                                   uint8_t *const *out, const size_t *cap, size_t *written);
+/* The same without the final wait: returns once everything is enqueued.  The compute stream is free as soon as
+ * the last render has run, so the NEXT sgx_mt_add_tracks* (uploads on a third stream, then analysis) overlaps the
+ * downloads still on the wire -- the two directions of the link are independent.  The host buffers are complete
+ * after sgx_mt_wait_images; a new request waits for the previous one first. */
+SGX_API int sgx_mt_get_spec_images_async(sgx_multitrack *mt, const size_t *id_list, size_t n_ids,
+                                         float px_per_sec, uint32_t nheight, int channels,
+                                         uint8_t *const *out, const size_t *cap, size_t *written);
+SGX_API int sgx_mt_wait_images(sgx_multitrack *mt);
+
 /* MultiTrack::get_wav_image(&self, id, px_per_sec, nheight, amp_min, amp_max) -> Vec<u8> (RGBA)
  * lib.rs:300-313, display.rs:63-115. */
 SGX_API int sgx_mt_get_wav_image(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t nheight,
@@ -182,11 +225,11 @@ SGX_API int sgx_mt_get_spec_db(sgx_multitrack *mt, size_t id, float *out, size_t
 SGX_API int sgx_mt_get_image_width(sgx_multitrack *mt, size_t id, float px_per_sec,
                                    uint32_t *nwidth);
 
-/* Multi-GPU hook: device pointer to two floats {max, -min} holding this handle's
- * LOCAL un-clamped dB extrema over its tracks (lib.rs:194-207).  A driver runs
- * all_reduce(MAX) on those 8 bytes on the handle's stream, then calls
- * sgx_mt_commit_range_device, which applies lib.rs:208-209 on the device.  Neither call
- * synchronises. */
+/* Multi-GPU hook for drivers that bring their own collective (sgx_mt_new_sharded / sgx_mt_attach_nccl do this
+ * inside the library): device pointer to four floats {max, -min, max_sr, max_sec} holding this handle's LOCAL
+ * un-clamped dB extrema (lib.rs:194-207) and metadata maxima.  A driver runs all_reduce(MAX) on them on the
+ * handle's stream, then calls sgx_mt_commit_range_device, which applies lib.rs:208-209 on the device.
+ * Neither call synchronises.  Single-device handles without an attached communicator only. */
 SGX_API int sgx_mt_range_device_ptr(sgx_multitrack *mt, float **d_max_negmin);
 SGX_API int sgx_mt_commit_range_device(sgx_multitrack *mt);
 /* Time-sharding ONE long track over several GPUs.  Every GPU owns a strip of output columns:

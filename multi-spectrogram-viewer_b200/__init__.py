@@ -75,6 +75,10 @@ PROTOTYPES = {
     "sgx_mt_new": (C.c_int, [C.POINTER(_vp)]),
     "sgx_mt_new_ex": (C.c_int, [C.POINTER(Settings), C.c_int, _vp, C.POINTER(_vp)]),
     "sgx_mt_free": (None, [_vp]),
+    "sgx_mt_new_sharded": (C.c_int, [C.POINTER(Settings), _pi, _sz, C.POINTER(_vp)]),
+    "sgx_nccl_unique_id": (C.c_int, [_pu8]),
+    "sgx_mt_attach_nccl": (C.c_int, [_vp, _pu8, C.c_int, C.c_int]),
+    "sgx_mt_get_device_count": (C.c_int, [_vp, _pi, _pi, _pi]),
     "sgx_mt_add_tracks": (C.c_int, [_vp, _psz, _sz, C.c_char_p, _pi]),
     "sgx_mt_add_tracks_pcm": (C.c_int, [_vp, _psz, _sz, C.POINTER(_vp), _psz, _pu32, _pu32, _pi]),
     "sgx_mt_add_tracks_pcm_i16": (C.c_int, [_vp, _psz, _sz, C.POINTER(_vp), _psz, _pu32, _pu32, _pi]),
@@ -84,6 +88,9 @@ PROTOTYPES = {
     "sgx_mt_get_spec_image_rgba": (C.c_int, [_vp, _sz, _f, _u32, _vp, _sz, _psz]),
     "sgx_mt_get_spec_image_device": (C.c_int, [_vp, _sz, _f, _u32, C.c_int, _vp, _sz, _psz]),
     "sgx_mt_get_spec_images_device": (C.c_int, [_vp, _psz, _sz, _f, _u32, C.c_int, C.POINTER(_vp), _psz, _psz]),
+    "sgx_mt_get_spec_images": (C.c_int, [_vp, _psz, _sz, _f, _u32, C.c_int, C.POINTER(_vp), _psz, _psz]),
+    "sgx_mt_get_spec_images_async": (C.c_int, [_vp, _psz, _sz, _f, _u32, C.c_int, C.POINTER(_vp), _psz, _psz]),
+    "sgx_mt_wait_images": (C.c_int, [_vp]),
     "sgx_mt_get_wav_image": (C.c_int, [_vp, _sz, _f, _u32, _f, _f, _vp, _sz, _psz]),
     "sgx_mt_get_frequency_hz": (C.c_int, [_vp, _sz, _f, _pf]),
     "sgx_mt_get_max_db": (C.c_int, [_vp, _pf]),
@@ -325,15 +332,51 @@ def _size_array(v: Iterable[int]):
     return (C.c_size_t * len(v))(*v), len(v)
 
 
-class MultiTrack:
-    """Mirror of the reference's ``MultiTrack`` class; one instance is bound to one GPU + stream."""
+def nccl_unique_id() -> bytes:
+    """128 bytes drawn on rank 0 and shipped to every rank before MultiTrack.attach_nccl (sgx_nccl_unique_id)."""
+    buf = (C.c_uint8 * 128)()
+    _check(_lib.sgx_nccl_unique_id(buf))
+    return bytes(buf)
 
-    def __init__(self, settings: Optional[Settings] = None, device: int = 0, stream: Optional[int] = None):
+
+class MultiTrack:
+    """Mirror of the reference's ``MultiTrack`` class.  ``device=d``: one GPU + stream.  ``devices=[...]`` (or
+    ``devices="all"``): one handle over several GPUs of this process, track t on devices[t mod G]
+    (sgx_mt_new_sharded).  ``attach_nccl`` joins the single-device handles of several processes."""
+
+    def __init__(self, settings: Optional[Settings] = None, device: int = 0, stream: Optional[int] = None, devices=None):
         self._h = _vp()
         self.device = device
         self.settings = settings if settings is not None else Settings.default()
-        _check(_lib.sgx_mt_new_ex(C.byref(self.settings), device, _vp(stream) if stream else None, C.byref(self._h)))
+        if devices is not None:
+            devs = [] if devices == "all" else [int(d) for d in devices]
+            arr = (C.c_int * max(1, len(devs)))(*devs)
+            _check(_lib.sgx_mt_new_sharded(C.byref(self.settings), arr if devs else None, len(devs), C.byref(self._h)))
+        else:
+            _check(_lib.sgx_mt_new_ex(C.byref(self.settings), device, _vp(stream) if stream else None, C.byref(self._h)))
         self._keep = {}  # id -> objects that must outlive the track (borrowed device tensors)
+        self._retired = []  # keepalives replaced while work that may still read them was only enqueued (sync=False)
+
+    def attach_nccl(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Collective over all ranks: this handle becomes shard `rank` of `world` (sgx_mt_attach_nccl)."""
+        buf = (C.c_uint8 * 128)(*unique_id)
+        _check(_lib.sgx_mt_attach_nccl(self._h, buf, rank, world))
+
+    def device_count(self):
+        """(engines inside the handle, rank, world)."""
+        n, r, w = C.c_int(), C.c_int(), C.c_int()
+        _check(_lib.sgx_mt_get_device_count(self._h, C.byref(n), C.byref(r), C.byref(w)))
+        return n.value, r.value, w.value
+
+    def _swap_keepalive(self, id, new, sync):
+        old = self._keep.pop(id, None)
+        if new is not None:
+            self._keep[id] = new
+        # enqueued kernels may still read the old buffer: it is released at the next synchronising call
+        if old is not None and not sync:
+            self._retired.append(old)
+        if sync:
+            self._retired.clear()
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -359,19 +402,22 @@ class MultiTrack:
         """Same as add_tracks with decoded audio: pcm[i] is [n] or interleaved [n, ch]; float32 or int16."""
         arrs = []
         for a in pcm:
+            if a is None:  # a track another rank owns (attached handles take the whole id list)
+                arrs.append(None)
+                continue
             a = np.asarray(a)
             if a.dtype != np.int16:
                 a = a.astype(np.float32, copy=False)
             arrs.append(np.ascontiguousarray(a))
-        kinds = {a.dtype == np.int16 for a in arrs}
+        kinds = {a.dtype == np.int16 for a in arrs if a is not None}
         if len(kinds) > 1:
             raise SgxError(SGX_ERR_BAD_ARG, "mix of int16 and float32 tracks in one call")
         fn = _lib.sgx_mt_add_tracks_pcm_i16 if kinds == {True} else _lib.sgx_mt_add_tracks_pcm
         ids, n = _size_array(id_list)
-        ptrs = (_vp * n)(*[a.ctypes.data for a in arrs])
-        ns, _ = _size_array(a.shape[0] for a in arrs)
+        ptrs = (_vp * n)(*[None if a is None else a.ctypes.data for a in arrs])
+        ns, _ = _size_array(0 if a is None else a.shape[0] for a in arrs)
         srs = (C.c_uint32 * n)(*[int(s) for s in sr])
-        chs = (C.c_uint32 * n)(*[1 if a.ndim == 1 else a.shape[1] for a in arrs])
+        chs = (C.c_uint32 * n)(*[0 if a is None else (1 if a.ndim == 1 else a.shape[1]) for a in arrs])
         ch = C.c_int()
         _check(fn(self._h, ids, n, ptrs, ns, srs, chs, C.byref(ch)))
         return bool(ch.value)
@@ -386,9 +432,8 @@ class MultiTrack:
         chs = (C.c_uint32 * n)(*([1] * n if channels is None else [int(c) for c in channels]))
         ch = C.c_int()
         _check(_lib.sgx_mt_add_tracks_pcm_device(self._h, ids, n, p, ns, srs, chs, C.byref(ch) if sync else None))
-        if keepalive is not None:
-            for i in id_list:
-                self._keep[i] = keepalive
+        for i in id_list:
+            self._swap_keepalive(i, keepalive, sync)
         return bool(ch.value) if sync else None
 
     def add_track_slice_device(self, id: int, ptr: int, chunk_offset: int, chunk_len: int, n_total: int, sr: int, channels: int,
@@ -396,8 +441,7 @@ class MultiTrack:
         """One time slice of a long track (device PCM, deferred; see sgx_mt_add_track_slice_device)."""
         _check(_lib.sgx_mt_add_track_slice_device(self._h, id, _vp(int(ptr)), chunk_offset, chunk_len, n_total, sr, channels,
                                                   frame_begin, frame_count))
-        if keepalive is not None:
-            self._keep[id] = keepalive
+        self._swap_keepalive(id, keepalive, False)
 
     def render_slice_device(self, id: int, px_per_sec: float, nheight: int, channels: int, ox_begin: int, ox_count: int,
                             out_ptr: int, cap: int) -> int:
@@ -409,7 +453,7 @@ class MultiTrack:
     def remove_track(self, id: int, sync: bool = True) -> Optional[bool]:
         ch = C.c_int()
         _check(_lib.sgx_mt_remove_track(self._h, id, C.byref(ch) if sync else None))
-        self._keep.pop(id, None)
+        self._swap_keepalive(id, None, sync)
         return bool(ch.value) if sync else None
 
     # -- images -------------------------------------------------------------------------------
@@ -431,6 +475,28 @@ class MultiTrack:
     def get_wav_image(self, id: int, px_per_sec: float, nheight: int, amp_min: float, amp_max: float) -> np.ndarray:
         """get_wav_image -> flat uint8 RGBA (lib.rs:300-313)."""
         return self._image(_lib.sgx_mt_get_wav_image, id, px_per_sec, nheight, 4, amp_min, amp_max)
+
+    def get_spec_images(self, id_list: Sequence[int], px_per_sec: float, nheight: int, channels: int = 3, out=None, wait: bool = True):
+        """get_spec_image for a list of tracks in one call (sgx_mt_get_spec_images): renders and device->host copies
+        are pipelined inside the library.  `out`: optional list of writable uint8 buffers (numpy arrays or objects with
+        a data_ptr(): pinned torch tensors make the copies asynchronous); returns the list of flat images.
+        wait=False returns after everything is enqueued -- call wait_images() before reading the buffers."""
+        ids, n = _size_array(id_list)
+        need = (C.c_size_t * n)()
+        _check(_lib.sgx_mt_get_spec_images(self._h, ids, n, px_per_sec, nheight, channels, None, None, need))
+        if out is None:
+            out = [np.empty(need[i], np.uint8) for i in range(n)]
+        ptrs = (_vp * n)(*[int(o.data_ptr()) if hasattr(o, "data_ptr") else o.ctypes.data for o in out])
+        caps, _ = _size_array(int(o.numel()) if hasattr(o, "numel") else o.size for o in out)
+        fn = _lib.sgx_mt_get_spec_images if wait else _lib.sgx_mt_get_spec_images_async
+        _check(fn(self._h, ids, n, px_per_sec, nheight, channels, ptrs, caps, need))
+        if not wait:
+            self._out_keep = out
+        return out
+
+    def wait_images(self) -> None:
+        _check(_lib.sgx_mt_wait_images(self._h))
+        self._out_keep = None
 
     def image_width(self, id: int, px_per_sec: float) -> int:
         w = C.c_uint32()
@@ -521,6 +587,7 @@ class MultiTrack:
     def synchronize(self) -> bool:
         ch = C.c_int()
         _check(_lib.sgx_mt_synchronize(self._h, C.byref(ch)))
+        self._retired.clear()
         return bool(ch.value)
 
 

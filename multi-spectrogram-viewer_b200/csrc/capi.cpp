@@ -1,7 +1,10 @@
 // capi.cpp -- the extern "C" boundary declared in include/sgx.h.  Every entry point catches all
 // exceptions and maps them to a status + thread-local message; nothing unwinds across the ABI.
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <vector>
 
 #include "engine.h"
 
@@ -9,9 +12,37 @@ using namespace sgx;
 
 static thread_local std::string g_last_error;
 
+// One handle = one engine per device.  sgx_mt_new / _ex: a single engine.  sgx_mt_new_sharded: an engine per listed
+// device inside this process, track id t on engine t mod G (lib.rs:161-166 parallelises over tracks; here the tracks
+// spread over GPUs), the engines joined by an NCCL communicator for the one exchange of the path (lib.rs:194-209).
 struct sgx_multitrack {
-    MultiTrack impl;
-    sgx_multitrack(const sgx_settings &s, int dev, cudaStream_t st) : impl(s, dev, st) {}
+    std::vector<std::unique_ptr<MultiTrack>> subs;
+    bool sharded() const { return subs.size() > 1; }
+    MultiTrack &one() // entry points that only make sense for a single engine
+    {
+        if (sharded()) throw Error(SGX_ERR_STATE, "not available on a multi-device handle (use one handle per device)");
+        return *subs[0];
+    }
+    MultiTrack &of(size_t id) { return *subs[id % subs.size()]; }
+    // the exchanges of all engines as one NCCL group (one host thread drives every device), then the commits
+    void exchange_and_commit(bool force_commit)
+    {
+        if (sharded()) {
+            nccl_check(nccl().GroupStart(), "ncclGroupStart");
+            for (auto &e : subs) e->exchange();
+            nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+            for (auto &e : subs) e->commit();
+        } else {
+            subs[0]->exchange();
+            if (force_commit || subs[0]->world() > 1) subs[0]->commit();
+        }
+    }
+    bool synchronize()
+    {
+        bool c = false;
+        for (auto &e : subs) c = e->synchronize() || c;
+        return c;
+    }
 };
 
 template <class F> static int guarded(F &&f)
@@ -75,7 +106,73 @@ int sgx_mt_new_ex(const sgx_settings *settings, int device, void *cuda_stream, s
         sgx_settings s;
         if (settings) s = *settings; else sgx_settings_default(&s);
         REQUIRE(s.freq_scale == SGX_FREQ_LINEAR || s.freq_scale == SGX_FREQ_MEL, "freq_scale");
-        *out = new sgx_multitrack(s, device, static_cast<cudaStream_t>(cuda_stream));
+        std::unique_ptr<sgx_multitrack> h(new sgx_multitrack());
+        h->subs.emplace_back(new MultiTrack(s, device, static_cast<cudaStream_t>(cuda_stream)));
+        *out = h.release();
+    });
+}
+
+int sgx_mt_new_sharded(const sgx_settings *settings, const int *devices, size_t n_devices, sgx_multitrack **out)
+{
+    return guarded([&] {
+        REQUIRE(out, "out is NULL");
+        *out = nullptr;
+        sgx_settings s;
+        if (settings) s = *settings; else sgx_settings_default(&s);
+        REQUIRE(s.freq_scale == SGX_FREQ_LINEAR || s.freq_scale == SGX_FREQ_MEL, "freq_scale");
+        std::vector<int> devs;
+        if (devices && n_devices) devs.assign(devices, devices + n_devices);
+        else { // every visible device
+            int count = 0;
+            if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); throw Error(SGX_ERR_CUDA, "no usable CUDA device (this engine has no CPU path)"); }
+            for (int d = 0; d < count; ++d) devs.push_back(d);
+        }
+        for (size_t i = 0; i < devs.size(); ++i)
+            for (size_t j = 0; j < i; ++j) REQUIRE(devs[i] != devs[j], "a device is listed twice");
+        std::unique_ptr<sgx_multitrack> h(new sgx_multitrack());
+        for (int d : devs) h->subs.emplace_back(new MultiTrack(s, d, nullptr));
+        if (devs.size() > 1) {
+            std::vector<NcclComm> comms(devs.size(), nullptr);
+            nccl_check(nccl().CommInitAll(comms.data(), (int)devs.size(), devs.data()), "ncclCommInitAll");
+            for (size_t g = 0; g < devs.size(); ++g) h->subs[g]->attach_comm(comms[g], (int)g, (int)devs.size(), true);
+        }
+        *out = h.release();
+    });
+}
+
+int sgx_nccl_unique_id(uint8_t out[128])
+{
+    return guarded([&] {
+        REQUIRE(out, "out is NULL");
+        NcclUniqueId id;
+        nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(out, id.internal, 128);
+    });
+}
+
+int sgx_mt_attach_nccl(sgx_multitrack *mt, const uint8_t unique_id[128], int rank, int world)
+{
+    return guarded([&] {
+        REQUIRE(mt && unique_id, "NULL argument");
+        REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+        MultiTrack &e = mt->one();
+        REQUIRE(e.world() == 1, "a communicator is already attached");
+        SGX_CUDA(cudaSetDevice(e.device()));
+        NcclUniqueId id;
+        std::memcpy(id.internal, unique_id, 128);
+        NcclComm comm = nullptr;
+        nccl_check(nccl().CommInitRank(&comm, world, id, rank), "ncclCommInitRank"); // collective over all ranks
+        e.attach_comm(comm, rank, world, true);
+    });
+}
+
+int sgx_mt_get_device_count(sgx_multitrack *mt, int *n_devices, int *rank, int *world)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        if (n_devices) *n_devices = (int)mt->subs.size();
+        if (rank) *rank = mt->sharded() ? 0 : mt->subs[0]->rank();
+        if (world) *world = mt->sharded() ? 1 : mt->subs[0]->world();
     });
 }
 
@@ -95,7 +192,15 @@ static int add_generic(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, 
         std::vector<PcmSource> srcs(n_ids);
         for (size_t i = 0; i < n_ids; ++i)
             srcs[i] = PcmSource{pcm[i], fmt, n_samples[i], sr[i], channels[i], on_device, std::string()};
-        const bool c = mt->impl.add_tracks(ids, srcs, changed != nullptr || !on_device);
+        const bool want = changed != nullptr || !on_device;
+        bool c = false;
+        if (mt->sharded()) {
+            for (auto &e : mt->subs) e->analyse_owned(ids, srcs);
+            mt->exchange_and_commit(true);
+            if (want) c = mt->synchronize();
+        } else {
+            c = mt->subs[0]->add_tracks(ids, srcs, want);
+        }
         if (changed) *changed = c ? 1 : 0;
     });
 }
@@ -136,16 +241,27 @@ int sgx_mt_add_tracks(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, c
             p = nl + 1;
         }
         const size_t n = std::min(n_ids, paths.size()); // zip stops at the shorter
-        std::vector<WavData> wavs(n);
-        for (size_t i = 0; i < n; ++i) wavs[i] = read_wav(paths[i]);
         std::vector<size_t> ids(id_list, id_list + n);
+        // a rank of a sharded job only opens the files of the tracks it owns (t mod world == rank)
+        std::vector<WavData> wavs(n);
         std::vector<PcmSource> srcs(n);
         for (size_t i = 0; i < n; ++i) {
+            bool mine = false;
+            for (auto &e : mt->subs) mine = mine || (mt->sharded() ? true : e->owns(ids[i]));
+            if (!mine) { srcs[i] = PcmSource{nullptr, PCM_F32, 0, 0, 0, false, paths[i]}; continue; }
+            wavs[i] = read_wav(paths[i]);
             const WavData &w = wavs[i];
             srcs[i] = PcmSource{w.is_i16 ? (const void *)w.i16.data() : (const void *)w.f32.data(),
                                 w.is_i16 ? PCM_I16 : PCM_F32, w.n, w.sr, w.ch, false, paths[i]};
         }
-        const bool c = mt->impl.add_tracks(ids, srcs, true);
+        bool c = false;
+        if (mt->sharded()) {
+            for (auto &e : mt->subs) e->analyse_owned(ids, srcs);
+            mt->exchange_and_commit(true);
+            c = mt->synchronize();
+        } else {
+            c = mt->subs[0]->add_tracks(ids, srcs, true);
+        }
         if (changed) *changed = c ? 1 : 0;
     });
 }
@@ -162,7 +278,7 @@ int sgx_mt_add_track_slice_device(sgx_multitrack *mt, size_t id, const float *d_
         srcs[0] = PcmSource{d_pcm, PCM_F32, chunk_len, sr, channels, true, std::string()};
         srcs[0].n_total = n_total; srcs[0].origin = chunk_offset;
         srcs[0].frame_begin = frame_begin; srcs[0].frame_count = frame_count;
-        mt->impl.add_tracks(ids, srcs, false);
+        mt->one().add_tracks(ids, srcs, false, true);
     });
 }
 
@@ -175,7 +291,7 @@ int sgx_mt_get_spec_image_slice_device(sgx_multitrack *mt, size_t id, float px_p
         uint8_t *outs[1] = {d_out};
         size_t caps[1] = {cap};
         std::vector<size_t> ids{id};
-        mt->impl.render(ids, px_per_sec, nheight, channels, d_out ? outs : nullptr, caps, written, &ox_begin, &ox_count);
+        mt->one().render(ids, px_per_sec, nheight, channels, d_out ? outs : nullptr, caps, written, &ox_begin, &ox_count);
     });
 }
 
@@ -212,7 +328,14 @@ int sgx_mt_remove_track(sgx_multitrack *mt, size_t id, int *changed)
 {
     return guarded([&] {
         REQUIRE(mt, "handle is NULL");
-        const bool c = mt->impl.remove_track(id, changed != nullptr);
+        bool c = false;
+        if (mt->sharded()) {
+            for (auto &e : mt->subs) e->drop(id); // the owner drops it, the others only refresh their local extrema
+            mt->exchange_and_commit(true);
+            if (changed) c = mt->synchronize();
+        } else {
+            c = mt->subs[0]->remove_track(id, changed != nullptr);
+        }
         if (changed) *changed = c ? 1 : 0;
     });
 }
@@ -222,11 +345,11 @@ static int spec_image_host(sgx_multitrack *mt, size_t id, float px_per_sec, uint
 {
     return guarded([&] {
         REQUIRE(mt, "handle is NULL");
-        const size_t need = (size_t)mt->impl.image_width(id, px_per_sec) * nheight * channels;
+        const size_t need = (size_t)mt->of(id).image_width(id, px_per_sec) * nheight * channels;
         if (written) *written = need;
         if (!out) return;
         if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
-        mt->impl.render_host(id, px_per_sec, nheight, channels, out, need);
+        mt->of(id).render_host(id, px_per_sec, nheight, channels, out, need);
     });
 }
 
@@ -258,7 +381,60 @@ int sgx_mt_get_spec_images_device(sgx_multitrack *mt, const size_t *id_list, siz
         REQUIRE(mt && (id_list || n_ids == 0), "NULL argument");
         REQUIRE(!d_out || cap, "cap is NULL");
         std::vector<size_t> ids(id_list, id_list + n_ids);
-        mt->impl.render(ids, px_per_sec, nheight, channels, d_out, cap, written);
+        if (!mt->sharded()) { mt->subs[0]->render(ids, px_per_sec, nheight, channels, d_out, cap, written); return; }
+        for (size_t g = 0; g < mt->subs.size(); ++g) { // every engine renders its own tracks into buffers of its own device
+            std::vector<size_t> sub, at;
+            for (size_t i = 0; i < n_ids; ++i) if (ids[i] % mt->subs.size() == g) { sub.push_back(ids[i]); at.push_back(i); }
+            if (sub.empty()) continue;
+            std::vector<uint8_t *> o(sub.size(), nullptr);
+            std::vector<size_t> c(sub.size(), 0), w(sub.size(), 0);
+            for (size_t k = 0; k < sub.size(); ++k) { if (d_out) o[k] = d_out[at[k]]; if (cap) c[k] = cap[at[k]]; }
+            mt->subs[g]->render(sub, px_per_sec, nheight, channels, d_out ? o.data() : nullptr, c.data(), w.data());
+            if (written) for (size_t k = 0; k < sub.size(); ++k) written[at[k]] = w[k];
+        }
+    });
+}
+
+static void images_async_all(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, float px_per_sec, uint32_t nheight,
+                             int channels, uint8_t *const *out, const size_t *cap, size_t *written)
+{
+    REQUIRE(mt && (id_list || n_ids == 0), "NULL argument");
+    REQUIRE(!out || cap, "cap is NULL");
+    REQUIRE(channels == 3 || channels == 4, "channels must be 3 or 4");
+    std::vector<size_t> ids(id_list, id_list + n_ids);
+    for (size_t g = 0; g < mt->subs.size(); ++g) {
+        std::vector<size_t> sub, at;
+        for (size_t i = 0; i < n_ids; ++i) if (ids[i] % mt->subs.size() == g) { sub.push_back(ids[i]); at.push_back(i); }
+        if (sub.empty()) continue;
+        std::vector<uint8_t *> o(sub.size(), nullptr);
+        std::vector<size_t> c(sub.size(), 0), w(sub.size(), 0);
+        for (size_t k = 0; k < sub.size(); ++k) { if (out) o[k] = out[at[k]]; if (cap) c[k] = cap[at[k]]; }
+        mt->subs[g]->images_async(sub, px_per_sec, nheight, channels, out ? o.data() : nullptr, c.data(), w.data());
+        if (written) for (size_t k = 0; k < sub.size(); ++k) written[at[k]] = w[k];
+    }
+}
+
+int sgx_mt_get_spec_images_async(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, float px_per_sec,
+                                 uint32_t nheight, int channels, uint8_t *const *out, const size_t *cap,
+                                 size_t *written)
+{
+    return guarded([&] { images_async_all(mt, id_list, n_ids, px_per_sec, nheight, channels, out, cap, written); });
+}
+
+int sgx_mt_wait_images(sgx_multitrack *mt)
+{
+    return guarded([&] {
+        REQUIRE(mt, "handle is NULL");
+        for (auto &e : mt->subs) e->wait_images();
+    });
+}
+
+int sgx_mt_get_spec_images(sgx_multitrack *mt, const size_t *id_list, size_t n_ids, float px_per_sec,
+                           uint32_t nheight, int channels, uint8_t *const *out, const size_t *cap, size_t *written)
+{
+    return guarded([&] {
+        images_async_all(mt, id_list, n_ids, px_per_sec, nheight, channels, out, cap, written);
+        for (auto &e : mt->subs) e->wait_images();
     });
 }
 
@@ -267,42 +443,42 @@ int sgx_mt_get_wav_image(sgx_multitrack *mt, size_t id, float px_per_sec, uint32
 {
     return guarded([&] {
         REQUIRE(mt, "handle is NULL");
-        const size_t need = (size_t)mt->impl.image_width(id, px_per_sec) * nheight * 4;
+        const size_t need = (size_t)mt->of(id).image_width(id, px_per_sec) * nheight * 4;
         if (written) *written = need;
         if (!out) return;
         if (cap < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
-        std::vector<uint8_t> img = mt->impl.wav_image(id, px_per_sec, nheight, amp_min, amp_max);
+        std::vector<uint8_t> img = mt->of(id).wav_image(id, px_per_sec, nheight, amp_min, amp_max);
         if (!img.empty()) std::memcpy(out, img.data(), img.size());
     });
 }
 
 int sgx_mt_get_frequency_hz(sgx_multitrack *mt, size_t id, float relative_freq, float *out)
 {
-    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.frequency_hz(id, relative_freq); });
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->of(id).frequency_hz(id, relative_freq); });
 }
 int sgx_mt_get_max_db(sgx_multitrack *mt, float *out)
 {
-    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.max_db(); });
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->subs[0]->max_db(); });
 }
 int sgx_mt_get_min_db(sgx_multitrack *mt, float *out)
 {
-    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.min_db(); });
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->subs[0]->min_db(); });
 }
 int sgx_mt_get_max_sec(sgx_multitrack *mt, float *out)
 {
-    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.max_sec(); });
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); float m = 0.0f; for (auto &e : mt->subs) m = std::max(m, e->max_sec()); *out = m; });
 }
 int sgx_mt_get_sec(sgx_multitrack *mt, size_t id, float *out)
 {
     return guarded([&] {
         REQUIRE(mt && out, "NULL argument");
-        const Track &t = mt->impl.track(id);
+        const Track &t = mt->of(id).track(id);
         *out = (float)t.n / (float)t.sr; // lib.rs:338
     });
 }
 int sgx_mt_get_sr(sgx_multitrack *mt, size_t id, uint32_t *out)
 {
-    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->impl.track(id).sr; });
+    return guarded([&] { REQUIRE(mt && out, "NULL argument"); *out = mt->of(id).track(id).sr; });
 }
 
 static void copy_string(const std::string &s, char *out, size_t cap, size_t *written)
@@ -314,13 +490,13 @@ static void copy_string(const std::string &s, char *out, size_t cap, size_t *wri
 }
 int sgx_mt_get_path(sgx_multitrack *mt, size_t id, char *out, size_t cap, size_t *written)
 {
-    return guarded([&] { REQUIRE(mt, "handle is NULL"); copy_string(mt->impl.track(id).path, out, cap, written); });
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); copy_string(mt->of(id).track(id).path, out, cap, written); });
 }
 int sgx_mt_get_filename(sgx_multitrack *mt, size_t id, char *out, size_t cap, size_t *written)
 {
     return guarded([&] {
         REQUIRE(mt, "handle is NULL");
-        const std::string &p = mt->impl.track(id).path;
+        const std::string &p = mt->of(id).track(id).path;
         const size_t slash = p.find_last_of('/');
         copy_string(slash == std::string::npos ? p : p.substr(slash + 1), out, cap, written);
     });
@@ -339,7 +515,7 @@ int sgx_mt_get_spec_shape(sgx_multitrack *mt, size_t id, size_t *n_frames, size_
 {
     return guarded([&] {
         REQUIRE(mt, "handle is NULL");
-        const Track &t = mt->impl.track(id);
+        const Track &t = mt->of(id).track(id);
         if (n_frames) *n_frames = t.n_frames;
         if (n_out) *n_out = t.n_out;
     });
@@ -349,49 +525,56 @@ int sgx_mt_get_spec_db(sgx_multitrack *mt, size_t id, float *out, size_t cap_ele
 {
     return guarded([&] {
         REQUIRE(mt, "handle is NULL");
-        const Track &t = mt->impl.track(id);
+        MultiTrack &e = mt->of(id);
+        const Track &t = e.track(id);
+        SGX_CUDA(cudaSetDevice(e.device()));
         const size_t need = t.n_frames * t.n_out;
         if (written_elems) *written_elems = need;
         if (!out) return;
         if (cap_elems < need) throw Error(SGX_ERR_BUFFER, "output buffer too small");
-        SGX_CUDA(cudaMemcpyAsync(out, t.spec.p, need * sizeof(float), cudaMemcpyDeviceToHost, mt->impl.stream()));
-        SGX_CUDA(cudaStreamSynchronize(mt->impl.stream()));
+        SGX_CUDA(cudaMemcpyAsync(out, t.spec.p, need * sizeof(float), cudaMemcpyDeviceToHost, e.stream()));
+        SGX_CUDA(cudaStreamSynchronize(e.stream()));
     });
 }
 
 int sgx_mt_get_image_width(sgx_multitrack *mt, size_t id, float px_per_sec, uint32_t *nwidth)
 {
-    return guarded([&] { REQUIRE(mt && nwidth, "NULL argument"); *nwidth = mt->impl.image_width(id, px_per_sec); });
+    return guarded([&] { REQUIRE(mt && nwidth, "NULL argument"); *nwidth = mt->of(id).image_width(id, px_per_sec); });
 }
 
 int sgx_mt_range_device_ptr(sgx_multitrack *mt, float **d_max_negmin)
 {
-    return guarded([&] { REQUIRE(mt && d_max_negmin, "NULL argument"); *d_max_negmin = mt->impl.range_device_ptr(); });
+    return guarded([&] { REQUIRE(mt && d_max_negmin, "NULL argument"); *d_max_negmin = mt->one().range_device_ptr(); });
 }
 int sgx_mt_commit_range_device(sgx_multitrack *mt)
 {
-    return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->impl.commit_range_device(); });
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->one().commit_range_device(); });
 }
 int sgx_mt_set_global_max_sr(sgx_multitrack *mt, uint32_t max_sr)
 {
-    return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->impl.set_global_max_sr(max_sr); });
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); for (auto &e : mt->subs) e->set_global_max_sr(max_sr); });
 }
 int sgx_mt_set_profiling(sgx_multitrack *mt, int on)
 {
-    return guarded([&] { REQUIRE(mt, "handle is NULL"); mt->impl.set_profiling(on != 0); });
+    return guarded([&] { REQUIRE(mt, "handle is NULL"); for (auto &e : mt->subs) e->set_profiling(on != 0); });
 }
 int sgx_mt_get_stage_times(sgx_multitrack *mt, float *analysis_ms, float *render_ms)
 {
     return guarded([&] {
         REQUIRE(mt && analysis_ms && render_ms, "NULL argument");
-        mt->impl.stage_times(analysis_ms, render_ms);
+        *analysis_ms = *render_ms = -1.0f;
+        for (auto &e : mt->subs) { // the slowest device
+            float a = -1.0f, r = -1.0f;
+            e->stage_times(&a, &r);
+            *analysis_ms = std::max(*analysis_ms, a); *render_ms = std::max(*render_ms, r);
+        }
     });
 }
 int sgx_mt_synchronize(sgx_multitrack *mt, int *changed)
 {
     return guarded([&] {
         REQUIRE(mt, "handle is NULL");
-        const bool c = mt->impl.synchronize();
+        const bool c = mt->synchronize();
         if (changed) *changed = c ? 1 : 0;
     });
 }

@@ -33,8 +33,10 @@ struct StftTrack {
     const int *mel_lo, *mel_cnt, *mel_off; // mel_lo points at packed int4 {lo, cnt, off, 0} per filter
     const float *mel_w;
     int mel_log2p;
-    const int *melp;       // block-padded copy of the bank (host_tables.h MelBands::packed), or null
-    int melp_nwb, melp_nblk; // its tap words and blocks: 32-bit words in total = nwb + 34 * nblk
+    const int *segp;       // segment form of the bank (host_tables.h MelBands::seg), or null when the bank is not mel-like
+    int seg_nwq, seg_nblk;   // its weight pairs and blocks
+    int seg_log2p;           // lanes cooperating on one segment
+    int seg_words;           // 32-bit words in total (pairs, lane and block descriptors, schedule)
     unsigned *range_slot;  // [2] order-preserving encodings of (max, min) dB; may be null
     int tile_begin;        // first CTA tile of this track inside the launch
 };
@@ -49,7 +51,7 @@ struct StftLaunch {
     int tile_floats;       // capacity of the staged tile
     int bank_floats;       // > 0: the CTA keeps the track's mel taps + descriptors in a region of its own
     int stereo_raw;        // 1: the launch holds f32 stereo tracks and its tiles have room for raw interleaved pairs
-    int warp2;             // 1: tiles were planned for the warp-per-frame-pair kernel (n_fft = 2048)
+    int warp2;             // > 0: tiles were planned for the warp-per-frame-pair kernel (n_fft = 2048) with that many warps
     const float2 *tw;      // [h]      exp(-2 pi i j / h)
     const float2 *split;   // [h/2+1]  (cos, sin)(k pi / h)                realfft.rs:88-93
 };

@@ -105,7 +105,9 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
         const int tpg = cfg.generic ? 1 : cfg.h / cfg.pts;
         // capacity of the imaginary plane of one group's exchange buffer (floats), where K1 stages the bank
         const size_t plane = cfg.generic ? 0 : cfg.fft_smem / sizeof(float) / (2 * (size_t)cfg.groups);
-        MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg, plane);
+        // the warp kernel walks all blocks with one warp and reads magnitude PAIRS; the block kernel spreads them
+        // over the warps of a group and reads vectors of cfg.vec frames
+        MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg, plane, cfg.warp2 ? 2 : cfg.vec);
         if (cfg.generic) mb.log2_split = 0;
         std::vector<int> meta(4 * n_mel, 0); // {lo, cnt, off, 0} per filter: one 16-byte load on the device
         for (size_t m = 0; m < n_mel; ++m) { meta[4 * m] = mb.lo[m]; meta[4 * m + 1] = mb.cnt[m]; meta[4 * m + 2] = mb.off[m]; }
@@ -114,8 +116,8 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
         tt.mel_w.upload(mb.w.data(), mb.w.size(), s);
         tt.mel_log2p = mb.log2_split;
         tt.mel_nnz = (int)mb.w.size();
-        tt.melp.upload(mb.packed.data(), mb.packed.size(), s);
-        tt.melp_nwb = mb.packed_nwb; tt.melp_nblk = mb.packed_nblk;
+        tt.segp.upload(mb.seg.data(), mb.seg.size(), s);
+        tt.seg_nwq = mb.seg_nwq; tt.seg_nblk = mb.seg_nblk; tt.seg_log2p = mb.seg_log2p; tt.seg_words = (int)mb.seg.size();
     }
     SGX_CUDA(cudaStreamSynchronize(s)); // host vectors die here
 }
@@ -131,7 +133,8 @@ static StftTrack make_desc(const void *d_pcm, int fmt, size_t n, uint32_t ch, si
     d.n_frames = (int)T; d.win_f = tt.win_f.p; d.out = out; d.n_out = (int)n_out;
     d.mel_lo = tt.mel_lo.p; d.mel_cnt = tt.mel_cnt.p; d.mel_off = tt.mel_off.p; d.mel_w = tt.mel_w.p;
     d.mel_log2p = tt.mel_log2p; d.range_slot = slot; d.tile_begin = 0;
-    d.melp = tt.melp_nblk > 0 ? tt.melp.p : nullptr; d.melp_nwb = tt.melp_nwb; d.melp_nblk = tt.melp_nblk;
+    d.segp = tt.seg_nblk > 0 ? tt.segp.p : nullptr; d.seg_nwq = tt.seg_nwq; d.seg_nblk = tt.seg_nblk;
+    d.seg_log2p = tt.seg_log2p; d.seg_words = tt.seg_words;
     return d;
 }
 
@@ -162,9 +165,9 @@ MultiTrack::MultiTrack(const sgx_settings &s, int device, cudaStream_t stream)
     slots_.alloc((size_t)n_slots_ * 2);
     SGX_CUDA(launch_range_init(slots_.p, n_slots_, stream_));
     for (int i = n_slots_ - 1; i >= 0; --i) free_slots_.push_back(i);
-    d_local_.alloc(2); d_state_.alloc(4);
-    const float st[4] = {-INFINITY, INFINITY, 0.0f, 0.0f}; // lib.rs:104-105
-    const float lc[2] = {-INFINITY, -INFINITY};
+    d_local_.alloc(4); d_state_.alloc(8);
+    const float st[8] = {-INFINITY, INFINITY, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; // lib.rs:104-105
+    const float lc[4] = {-INFINITY, -INFINITY, 0.0f, 0.0f};
     SGX_CUDA(cudaMemcpyAsync(d_state_.p, st, sizeof(st), cudaMemcpyHostToDevice, stream_));
     SGX_CUDA(cudaMemcpyAsync(d_local_.p, lc, sizeof(lc), cudaMemcpyHostToDevice, stream_));
     SGX_CUDA(cudaStreamSynchronize(stream_));
@@ -178,6 +181,11 @@ MultiTrack::~MultiTrack()
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     for (auto &e : copy_events_) cudaEventDestroy(e);
     if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+    if (out_stream_) { cudaStreamSynchronize(out_stream_); cudaStreamDestroy(out_stream_); }
+    if (out_ev_) cudaEventDestroy(out_ev_);
+    if (out_done_) cudaEventDestroy(out_done_);
+    d_imgs_.clear();
+    if (comm_ && comm_owned_) { try { nccl().CommDestroy(comm_); } catch (...) {} }
     if (own_stream_) cudaStreamDestroy(stream_);
 }
 
@@ -252,27 +260,53 @@ void MultiTrack::drop_track(size_t id)
     tracks_.erase(it);
 }
 
-void MultiTrack::reduce_and_commit(bool commit)
+void MultiTrack::reduce_local()
 {
-    SGX_CUDA(launch_range_reduce(slots_.p, n_slots_, d_local_.p, stream_));
-    // deferred mode: a multi-GPU driver all-reduces d_local_ first and commits afterwards
-    if (commit) { SGX_CUDA(launch_range_commit(d_local_.p, set_.db_range, d_state_.p, stream_)); pending_ = true; }
+    // lib.rs:220-224 / 178-182: metadata maxima over ALL tracks this handle holds, recomputed on every add and remove
+    uint32_t msr = 0;
+    for (auto &kv : tracks_) msr = std::max(msr, kv.second.sr);
+    if (msr != max_sr_) { max_sr_ = msr; changed_acc_ = true; }
+    SGX_CUDA(launch_range_reduce(slots_.p, n_slots_, d_local_.p, (float)max_sr_, max_sec_, stream_));
 }
 
-void MultiTrack::commit_range_device()
+void MultiTrack::attach_comm(NcclComm comm, int rank, int world, bool owned)
 {
+    if (world < 1 || rank < 0 || rank >= world) throw Error(SGX_ERR_BAD_ARG, "attach: bad rank / world");
+    if (!tracks_.empty()) throw Error(SGX_ERR_STATE, "attach a communicator before the first track is added");
+    comm_ = comm; comm_owned_ = owned; rank_ = rank; world_ = world;
+}
+
+void MultiTrack::exchange()
+{
+    if (!comm_) return;
+    SGX_CUDA(cudaSetDevice(device_));
+    // {max, -min, max_sr, max_sec}: 16 bytes, MAX, in place, on the stream that carries K1 and K3 -- the render that
+    // follows is ordered behind it on the device; no host round trip (lib.rs:194-209 across shards)
+    nccl_check(nccl().AllReduce(d_local_.p, d_local_.p, 4, kNcclFloat32, kNcclMax, comm_, stream_), "ncclAllReduce");
+}
+
+void MultiTrack::commit()
+{
+    SGX_CUDA(cudaSetDevice(device_));
     SGX_CUDA(launch_range_commit(d_local_.p, set_.db_range, d_state_.p, stream_));
     pending_ = true;
 }
+
+void MultiTrack::commit_range_device() { commit(); }
 
 bool MultiTrack::synchronize()
 {
     SGX_CUDA(cudaSetDevice(device_));
     if (pending_) {
-        float st[4];
+        float st[8];
         SGX_CUDA(cudaMemcpyAsync(st, d_state_.p, sizeof(st), cudaMemcpyDeviceToHost, stream_));
         SGX_CUDA(cudaStreamSynchronize(stream_));
         max_db_ = st[0]; min_db_ = st[1];
+        if (comm_) { // what the other shards hold (lib.rs:220-224, 178-182)
+            const uint32_t gsr = (uint32_t)st[3];
+            if (!global_sr_fixed_ && gsr != global_max_sr_) { global_max_sr_ = gsr; changed_acc_ = true; }
+            global_max_sec_ = st[4];
+        }
         if (st[2] != 0.0f) {
             changed_acc_ = true;
             const float zero = 0.0f;
@@ -290,7 +324,29 @@ bool MultiTrack::synchronize()
 
 uint32_t MultiTrack::effective_max_sr() const { return global_max_sr_ ? std::max(global_max_sr_, max_sr_) : max_sr_; }
 
-bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs, bool want_changed)
+bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs, bool want_changed, bool sliced)
+{
+    if (ids.size() != srcs.size()) throw Error(SGX_ERR_BAD_ARG, "id_list and track list differ in length");
+    if (sliced) analyse(ids, srcs); else analyse_owned(ids, srcs);
+    exchange();
+    // without a communicator and without a waiting caller the range stays uncommitted: a driver that shards by its
+    // own means all-reduces range_device_ptr() in-stream and calls commit_range_device()
+    if (want_changed || comm_) commit();
+    if (!want_changed) return false;
+    return synchronize();
+}
+
+void MultiTrack::analyse_owned(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs)
+{
+    if (ids.size() != srcs.size()) throw Error(SGX_ERR_BAD_ARG, "id_list and track list differ in length");
+    if (world_ <= 1) { analyse(ids, srcs); return; }
+    std::vector<size_t> mine; // track t lives where t % world == rank
+    std::vector<PcmSource> msrc;
+    for (size_t i = 0; i < ids.size(); ++i) if (owns(ids[i])) { mine.push_back(ids[i]); msrc.push_back(srcs[i]); }
+    analyse(mine, msrc);
+}
+
+void MultiTrack::analyse(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs)
 {
     SGX_CUDA(cudaSetDevice(device_));
     if (ids.size() != srcs.size()) throw Error(SGX_ERR_BAD_ARG, "id_list and track list differ in length");
@@ -305,6 +361,16 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         if (s.n_total) { // time slice of a longer track
             if (s.origin + s.n > s.n_total || s.frame_count == 0 || s.frame_begin + s.frame_count > (size_t)pre[i].T)
                 throw Error(SGX_ERR_BAD_ARG, "time slice outside the track");
+            // the chunk must hold every sample its frames read, reflections at the ends of the track included
+            // (the loader clamps silently otherwise); same arithmetic as sgx_slice_plan without its slack
+            const long long n = (long long)s.n_total, pad_l = (long long)(pre[i].n_fft - pre[i].win) / 2;
+            long long lo = (long long)s.frame_begin * (long long)pre[i].hop - (long long)(pre[i].win / 2) - pad_l;
+            long long hi = (long long)(s.frame_begin + s.frame_count - 1) * (long long)pre[i].hop - (long long)(pre[i].win / 2) - pad_l + (long long)pre[i].n_fft;
+            if (lo < 0) hi = std::max(hi, -lo + 1);
+            if (hi > n) lo = std::min(lo, 2 * (n - 1) - (hi - 1));
+            lo = std::max(0LL, std::min(lo, n)); hi = std::max(0LL, std::min(hi, n));
+            if ((long long)s.origin > lo || (long long)(s.origin + s.n) < hi)
+                throw Error(SGX_ERR_BAD_ARG, "time slice does not hold the samples its frames read (see sgx_slice_plan)");
         }
     }
     // ---- insert tracks (lib.rs:174-187) --------------------------------------------------------------
@@ -371,14 +437,16 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
         if (set_.freq_scale == SGX_FREQ_MEL)
             for (size_t id : kv.second) {
                 const TrackTables &tt = *tracks_.at(id).tables;
-                bank_floats = std::max(bank_floats, cfg.fused ? tt.melp_words() : ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel);
+                bank_floats = std::max(bank_floats, tt.bank_floats(cfg.fused));
             }
         int sample_floats = 1; // f32 stereo tracks stage raw interleaved pairs: twice the room per sample
+        bool warp2_ok = true;
         for (size_t id : kv.second) {
             const Track &t = tracks_.at(id);
             if (set_.freq_scale == SGX_FREQ_MEL && t.ch == 2 && t.fmt == PCM_F32) sample_floats = 2;
+            if (set_.freq_scale == SGX_FREQ_MEL && t.tables->seg_nblk == 0) warp2_ok = false;
         }
-        Group g{kv.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats, sample_floats), 0};
+        Group g{kv.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats, sample_floats, warp2_ok), 0};
         // a track id may appear twice in id_list; the last one wins, launch it once
         std::vector<size_t> uniq;
         for (size_t id : kv.second) if (std::find(uniq.begin(), uniq.end(), id) == uniq.end()) uniq.push_back(id);
@@ -419,19 +487,26 @@ bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSourc
     }
     if (profiling_) { SGX_CUDA(cudaEventRecord(ev_[1], stream_)); ev_valid_[0] = true; }
     // ---- update_spec_greys, range part (lib.rs:193-229) ------------------------------------------------
-    reduce_and_commit(want_changed);
-    uint32_t msr = 0;
-    for (auto &kv : tracks_) msr = std::max(msr, kv.second.sr);
-    if (msr != max_sr_) { max_sr_ = msr; changed_acc_ = true; }
-    if (!want_changed) return false;
-    return synchronize();
+    reduce_local();
 }
 
 bool MultiTrack::remove_track(size_t id, bool want_changed)
 {
+    drop(id);
+    exchange();
+    if (want_changed || comm_) commit();
+    if (!want_changed) return false;
+    return synchronize();
+}
+
+void MultiTrack::drop(size_t id)
+{
     SGX_CUDA(cudaSetDevice(device_));
     auto it = tracks_.find(id);
-    if (it == tracks_.end()) throw Error(SGX_ERR_UNKNOWN_ID, "remove_track: unknown track id " + std::to_string(id));
+    if (it == tracks_.end()) {
+        if (!owns(id)) { reduce_local(); return; } // another shard's track: only the exchange concerns this handle
+        throw Error(SGX_ERR_UNKNOWN_ID, "remove_track: unknown track id " + std::to_string(id));
+    }
     drop_track(id);
     if (id_max_sec_ == id) { // lib.rs:269-286
         size_t best_id = 0; float best = 0.0f;
@@ -441,12 +516,7 @@ bool MultiTrack::remove_track(size_t id, bool want_changed)
         }
         id_max_sec_ = best_id; max_sec_ = best;
     }
-    reduce_and_commit(want_changed);
-    uint32_t msr = 0;
-    for (auto &kv : tracks_) msr = std::max(msr, kv.second.sr);
-    if (msr != max_sr_) { max_sr_ = msr; changed_acc_ = true; }
-    if (!want_changed) return false;
-    return synchronize();
+    reduce_local();
 }
 
 const Track &MultiTrack::track(size_t id) const
@@ -493,6 +563,10 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
     if (channels != 3 && channels != 4) throw Error(SGX_ERR_BAD_ARG, "channels must be 3 or 4");
     if (nheight > 65535u) throw Error(SGX_ERR_BAD_ARG, "nheight too large");
     const bool mel = set_.freq_scale == SGX_FREQ_MEL;
+    // the image geometry depends on the highest sample rate of ALL shards (lib.rs:220-248): with a communicator it
+    // arrives with the range exchange and is read back here (one stream synchronisation per add / remove) unless
+    // the driver supplied it with set_global_max_sr
+    if (comm_ && pending_ && !global_sr_fixed_) synchronize_keep_changed();
     const uint32_t msr = effective_max_sr();
     // The axis-table cache is bounded, but it is only ever emptied HERE, before this call resolves its first key:
     // descriptors assembled below hold raw pointers into it (and launches already enqueued read its device tables,
@@ -579,6 +653,59 @@ void MultiTrack::render_host(size_t id, float px_per_sec, uint32_t nheight, int 
     render({id}, px_per_sec, nheight, channels, outs, caps, wr);
     SGX_CUDA(cudaMemcpyAsync(out, d_img_.p, need, cudaMemcpyDeviceToHost, stream_));
     SGX_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void MultiTrack::images_async(const std::vector<size_t> &ids, float px_per_sec, uint32_t nheight, int channels,
+                              uint8_t *const *out, const size_t *cap, size_t *written)
+{
+    SGX_CUDA(cudaSetDevice(device_));
+    wait_images(); // the staging buffers of the previous request are being read by its copies
+    std::vector<size_t> need(ids.size(), 0);
+    bool short_buf = false;
+    for (size_t i = 0; i < ids.size(); ++i) {
+        need[i] = (size_t)image_width(ids[i], px_per_sec) * nheight * (size_t)channels;
+        if (written) written[i] = need[i];
+        if (out && out[i] && cap[i] < need[i]) short_buf = true;
+    }
+    if (!out) return; // size query
+    if (short_buf) throw Error(SGX_ERR_BUFFER, "output buffer too small");
+    if (!out_stream_) {
+        SGX_CUDA(cudaStreamCreateWithFlags(&out_stream_, cudaStreamNonBlocking));
+        SGX_CUDA(cudaEventCreateWithFlags(&out_ev_, cudaEventDisableTiming));
+        SGX_CUDA(cudaEventCreateWithFlags(&out_done_, cudaEventDisableTiming));
+    }
+    // one staging buffer per image: every render of the batch is enqueued at once (K3 of image i+1 runs while the copy
+    // of image i is on the wire), and the compute stream is free again after the last render -- the uploads and K1 of
+    // the next add_tracks then overlap the rest of the downloads (the two directions of the link are independent)
+    if (d_imgs_.size() < ids.size()) d_imgs_.resize(ids.size());
+    std::vector<uint8_t *> d_out(ids.size(), nullptr);
+    std::vector<size_t> caps(ids.size(), 0), wr(ids.size(), 0);
+    for (size_t i = 0; i < ids.size(); ++i) {
+        if (!out[i] || need[i] == 0) continue;
+        d_imgs_[i].ensure(need[i]);
+        d_out[i] = d_imgs_[i].p; caps[i] = need[i];
+    }
+    // renders in chunks of a few images so that the first copy starts early
+    const size_t chunk = 4;
+    for (size_t a = 0; a < ids.size(); a += chunk) {
+        const size_t b = std::min(ids.size(), a + chunk);
+        std::vector<size_t> sub(ids.begin() + a, ids.begin() + b);
+        render(sub, px_per_sec, nheight, channels, d_out.data() + a, caps.data() + a, wr.data() + a);
+        SGX_CUDA(cudaEventRecord(out_ev_, stream_));
+        SGX_CUDA(cudaStreamWaitEvent(out_stream_, out_ev_, 0));
+        for (size_t i = a; i < b; ++i)
+            if (d_out[i]) SGX_CUDA(cudaMemcpyAsync(out[i], d_out[i], need[i], cudaMemcpyDeviceToHost, out_stream_));
+    }
+    SGX_CUDA(cudaEventRecord(out_done_, out_stream_));
+    out_pending_ = true;
+}
+
+void MultiTrack::wait_images()
+{
+    if (!out_pending_) return;
+    SGX_CUDA(cudaSetDevice(device_));
+    SGX_CUDA(cudaEventSynchronize(out_done_));
+    out_pending_ = false;
 }
 
 void MultiTrack::set_profiling(bool on)
@@ -697,7 +824,7 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     d_in.ensure(n + 16); d_out.ensure(elems);
     SGX_CUDA(cudaMemcpyAsync(d_in.p, input, n * sizeof(float), cudaMemcpyHostToDevice, s));
     StftTrack d = make_desc(d_in.p, PCM_F32, n, 1, win, hop, n_fft, (size_t)T, tt, d_out.p, n_out, nullptr);
-    const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop, mode != MODE_MEL_DB ? 0 : (pl.cfg.fused ? tt.melp_words() : ((tt.mel_nnz + 3) & ~3) + 4 * (int)tt.n_mel));
+    const StftTiling tl = plan_stft_tiles(pl.cfg, (int)hop, mode != MODE_MEL_DB ? 0 : tt.bank_floats(pl.cfg.fused), 1, mode != MODE_MEL_DB || tt.seg_nblk > 0);
     DevBuf<StftTrack> &dd = ws.desc; dd.upload(&d, 1, s);
     StftLaunch L{};
     L.tracks = dd.p; L.n_tracks = 1;

@@ -15,6 +15,7 @@
 #include "../../include/sgx.h"
 #include "host_tables.h"
 #include "kernels.h"
+#include "nccl_dyn.h"
 
 namespace sgx {
 
@@ -67,9 +68,10 @@ struct TrackTables {
     DevBuf<float> mel_w;
     int mel_log2p = 0;
     int mel_nnz = 0;
-    DevBuf<int> melp;                      // block-padded copy of the bank (MelBands::packed)
-    int melp_nwb = 0, melp_nblk = 0;
-    int melp_words() const { return melp_nwb + 34 * melp_nblk; }
+    DevBuf<int> segp;                      // segment form of the bank (MelBands::seg); empty when the bank is not mel-like
+    int seg_nwq = 0, seg_nblk = 0, seg_log2p = 0, seg_words = 0;
+    // shared-memory floats a K1 launch reserves for the bank of this track
+    int bank_floats(bool fused) const { return fused && seg_nblk > 0 ? seg_words : ((mel_nnz + 3) & ~3) + 4 * (int)n_mel; }
 };
 
 struct AxisTableDev {
@@ -120,8 +122,30 @@ public:
     ~MultiTrack();
 
     // lib.rs:171-191.  want_changed == false: no host synchronisation.
-    bool add_tracks(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs, bool want_changed);
+    // `sliced`: the sources are time slices of tracks every shard holds a piece of (n3): no ownership filter
+    bool add_tracks(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs, bool want_changed, bool sliced = false);
     bool remove_track(size_t id, bool want_changed);    // lib.rs:265-292
+    // ---- sharding: the tracks of a batch spread over several handles -- GPUs of one process or ranks ----
+    // With a communicator attached, track `id` lives on the handle with id % world == rank; add_tracks takes the
+    // WHOLE id list on every handle and keeps its own share, remove_track of a foreign id only joins the exchange.
+    // Every add / remove then all-reduces {max, -min, max_sr, max_sec} in-stream before the range is committed.
+    void attach_comm(NcclComm comm, int rank, int world, bool owned);
+    bool owns(size_t id) const { return world_ <= 1 || (int)(id % (size_t)world_) == rank_; }
+    int rank() const { return rank_; }
+    int world() const { return world_; }
+    // the phases of add_tracks / remove_track, exposed so that a multi-device handle can issue the exchanges of its
+    // sub-engines as one NCCL group:  analyse | drop  ->  exchange  ->  commit  [-> synchronize]
+    void analyse(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs);
+    void analyse_owned(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs); // this handle's share of a batch
+    void drop(size_t id);
+    void exchange();
+    void commit();
+    // batched host-buffer images (lib.rs:294-298 for a list of ids): renders go to per-image device staging, the
+    // device->host copies run on a second stream under the remaining renders -- and under the uploads of the NEXT
+    // add_tracks; wait_images blocks until the host buffers of the last request are complete
+    void images_async(const std::vector<size_t> &ids, float px_per_sec, uint32_t nheight, int channels,
+                      uint8_t *const *out, const size_t *cap, size_t *written);
+    void wait_images();
     // lib.rs:294-298 (channels 3) / RGBA; device output, asynchronous
     void render(const std::vector<size_t> &ids, float px_per_sec, uint32_t nheight, int channels,
                 uint8_t *const *d_out, const size_t *cap, size_t *written, const uint32_t *ox_begin = nullptr,
@@ -133,15 +157,17 @@ public:
 
     const Track &track(size_t id) const;
     bool synchronize();                                 // returns `changed` accumulated since last call
-    float max_db() { synchronize(); return max_db_; }
-    float min_db() { synchronize(); return min_db_; }
-    float max_sec() const { return max_sec_; }
+    void synchronize_keep_changed() { const bool c = synchronize(); changed_acc_ = changed_acc_ || c; }
+    float max_db() { synchronize_keep_changed(); return max_db_; }
+    float min_db() { synchronize_keep_changed(); return min_db_; }
+    float max_sec() { if (comm_) synchronize_keep_changed(); return world_ > 1 ? std::max(max_sec_, global_max_sec_) : max_sec_; }
     float frequency_hz(size_t id, float rel) const;     // lib.rs:315-322
     uint32_t image_width(size_t id, float px_per_sec) const;
     float *range_device_ptr() { return d_local_.p; }
     void commit_range_device();
-    void set_global_max_sr(uint32_t sr) { global_max_sr_ = sr; }
+    void set_global_max_sr(uint32_t sr) { global_max_sr_ = sr; global_sr_fixed_ = sr != 0; }
     cudaStream_t stream() const { return stream_; }
+    int device() const { return device_; }
     const sgx_settings &settings() const { return set_; }
     void derive_params(uint32_t sr, size_t *win, size_t *hop, size_t *n_fft) const;
 
@@ -149,7 +175,7 @@ private:
     TrackTables *tables_for(uint32_t sr, size_t win, size_t n_fft);
     AxisTableDev *axis_table(int n_in, int n_out, bool tap_major);
     void drop_track(size_t id);
-    void reduce_and_commit(bool commit);
+    void reduce_local();
     int alloc_slot();
     uint32_t effective_max_sr() const;
 
@@ -164,8 +190,8 @@ private:
     DevBuf<unsigned> slots_;
     std::vector<int> free_slots_;
     int n_slots_ = 0;
-    DevBuf<float> d_local_;  // {max, -min} over local tracks (un-clamped)
-    DevBuf<float> d_state_;  // {max_db, min_db, changed flag}  sticky like lib.rs:210-218
+    DevBuf<float> d_local_;  // {max, -min, max_sr, max_sec} over local tracks (un-clamped); all-reduced in place
+    DevBuf<float> d_state_;  // {max_db, min_db, changed flag, max_sr, max_sec}  sticky like lib.rs:210-218
     DevBuf<StftTrack> d_stft_;
     DevBuf<RenderTrack> d_render_;
     DevBuf<uint8_t> d_img_;      // staging for host-buffer image requests
@@ -173,6 +199,15 @@ private:
     bool profiling_ = false, ev_valid_[2] = {false, false};
     cudaStream_t copy_stream_ = nullptr;          // H2D uploads of host-resident PCM
     std::vector<cudaEvent_t> copy_events_;
+    cudaStream_t out_stream_ = nullptr;           // D2H copies of rendered images
+    cudaEvent_t out_ev_ = nullptr, out_done_ = nullptr;
+    bool out_pending_ = false;
+    std::vector<DevBuf<uint8_t>> d_imgs_;         // per-image staging of images_async
+    NcclComm comm_ = nullptr;
+    bool comm_owned_ = false;
+    int rank_ = 0, world_ = 1;
+    float global_max_sec_ = 0.0f;
+    bool global_sr_fixed_ = false;
     float max_db_, min_db_;
     float max_sec_ = 0.0f;
     size_t id_max_sec_ = 0;

@@ -181,8 +181,149 @@ void lanczos3_span(uint32_t n_in, uint32_t n_out, uint32_t o, uint32_t *left, ui
     *left = (uint32_t)l; *right = (uint32_t)r;
 }
 
+// Segment form of a mel-like bank (MelBands::seg).  A triangular bank touches every bin with at most two
+// NEIGHBOURING filters: the falling side of filter s-1 and the rising side of filter s.  "Segment s" is the run of
+// bins for which that holds; a lane that walks segment s reads each magnitude ONCE and feeds two accumulators,
+// U_s (rising weights, -> filter s) and D_s (falling weights, -> filter s-1); filter m is U_m + D_(m+1).  Against the
+// filter-major form (every magnitude read twice, every filter as long as two segments) this halves both the
+// shared-memory reads and the tap iterations of the projection.  Returns false (and leaves mb.seg empty) when the
+// bank does not have that structure; the kernels then use the banded form.
+static bool build_mel_segments(MelBands &mb, const float *fb, size_t n_freq, size_t n_mel, int warps, int vec)
+{
+    mb.seg.clear(); mb.seg_nwq = mb.seg_nblk = 0; mb.seg_log2p = 0;
+    if (n_mel == 0 || n_mel >= 0xfffe || n_freq > 0xffff) return false;
+    const size_t S = n_mel + 1; // segments
+    // ---- bin -> segment ---------------------------------------------------------------------------------
+    std::vector<int> seg_of(n_freq, -1);
+    for (size_t k = 0; k < n_freq; ++k) {
+        int f0 = -1, nf = 0;
+        for (size_t m = 0; m < n_mel; ++m)
+            if (fb[k * n_mel + m] != 0.0f) { if (nf == 0) f0 = (int)m; else if ((int)m != f0 + 1 || nf > 1) return false; ++nf; }
+        if (nf == 2) seg_of[k] = f0 + 1;
+        else if (nf == 1) { // rising side of f0 up to and including its peak, falling side after it
+            const int lo = mb.lo[f0], c = mb.cnt[f0];
+            int peak = lo;
+            for (int j = 1; j < c; ++j) if (mb.w[mb.off[f0] + j] > mb.w[mb.off[f0] + peak - lo]) peak = lo + j;
+            seg_of[k] = (int)k <= peak ? f0 : f0 + 1;
+        }
+    }
+    std::vector<int> first(S, -1), len(S, 0);
+    int prev = -1;
+    for (size_t k = 0; k < n_freq; ++k) {
+        const int sg = seg_of[k];
+        if (sg < 0) continue;
+        if (sg < prev) return false;                                   // segments must rise with the bins
+        if (len[sg] > 0 && first[sg] + len[sg] != (int)k) return false; // and be contiguous
+        if (len[sg] == 0) first[sg] = (int)k;
+        ++len[sg];
+        prev = sg;
+    }
+    { // empty segments sit where their neighbours meet (their weights are zero anyway)
+        int at = 0;
+        for (size_t sg = 0; sg < S; ++sg) { if (len[sg] == 0) first[sg] = at; else at = first[sg] + len[sg]; }
+    }
+    // ---- lanes per segment: tap iterations + fixed cost per block of 32 lanes -----------------------------
+    int best_lg = 0; double best_cost = 1e300;
+    for (int lg = 0; lg <= 4; ++lg) {
+        const int P = 1 << lg, U = 32 / P, outs = U - 1;
+        double cost = 0.0;
+        for (size_t s0 = 0; s0 < n_mel; s0 += outs) {
+            int longest = 0;
+            for (size_t sg = s0; sg < std::min(S, s0 + U); ++sg) longest = std::max(longest, (len[sg] + P - 1) / P);
+            cost += std::max(2, (longest + 1) & ~1) + 5.0 + 1.0 * lg;
+        }
+        if (cost < best_cost) { best_cost = cost; best_lg = lg; }
+    }
+    const int lg = best_lg, P = 1 << lg, U = 32 / P, outs = U - 1;
+    const size_t n_blocks = (n_mel + outs - 1) / outs;
+    // magnitudes sit at their bin index as vectors of `vec` floats: a shared-memory phase serves 32 / vec lanes,
+    // which collide when their bins agree modulo that number
+    const int phase = std::max(1, 32 / std::max(1, vec)), mod = phase;
+    const int limit = (int)n_freq; // every read stays inside [0, n_freq)
+    struct Blk { int off, nj; std::vector<int> q; };
+    std::vector<Blk> blks(n_blocks);
+    size_t nwq = 0;
+    for (size_t b = 0; b < n_blocks; ++b) {
+        Blk &B = blks[b];
+        int nj = 2;
+        for (int u = 0; u < U; ++u) { const size_t sg = b * outs + u; if (sg < S) nj = std::max(nj, ((len[sg] + P - 1) / P + 1) & ~1); }
+        for (;; nj += 2) { // shifts: a window may start q P bins early on zero weights (free while it stays within nj taps)
+            if ((nj + 1) * P > (int)n_freq) return false; // degenerate (a handful of bins): the banded form serves
+            B.q.assign(U, 0);
+            bool ok = true;
+            std::vector<unsigned long long> occ((U * P + phase - 1) / phase, 0ull); // residues taken per phase
+            for (int u = 0; u < U && ok; ++u) {
+                const size_t sg = b * outs + u;
+                const int f = sg < S ? first[sg] : limit - 1, need = sg < S ? (len[sg] + P - 1) / P : 0;
+                const int q_hi = std::min(nj - need, f / P);
+                const int over = f + (P - 1) + (nj - 1) * P - (limit - 1);
+                const int q_lo = over > 0 ? (over + P - 1) / P : 0;
+                if (q_lo > q_hi) { ok = false; break; }
+                int best_q = q_lo, best_c = 1 << 30;
+                for (int q = q_lo; q <= q_hi; ++q) {
+                    int c = 0;
+                    for (int pl = 0; pl < P; ++pl) {
+                        const int lane = u * P + pl;
+                        if ((occ[lane / phase] >> ((f + pl - q * P) % mod)) & 1ull) ++c;
+                    }
+                    c = c * 64 + (q - q_lo);
+                    if (c < best_c) { best_c = c; best_q = q; }
+                }
+                B.q[u] = best_q;
+                for (int pl = 0; pl < P; ++pl) { const int lane = u * P + pl; occ[lane / phase] |= 1ull << ((f + pl - best_q * P) % mod); }
+            }
+            if (ok) break;
+        }
+        B.off = (int)nwq; B.nj = nj;
+        nwq += (size_t)32 * nj;
+    }
+    // ---- schedule: blocks longest-first onto the warps of a thread group ------------------------------------
+    std::vector<std::pair<int, int>> cost(n_blocks);
+    for (size_t b = 0; b < n_blocks; ++b) cost[b] = {blks[b].nj + 6, (int)b};
+    std::sort(cost.begin(), cost.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+    std::vector<std::vector<int>> lists(warps);
+    std::vector<long> load(warps, 0);
+    for (auto &c : cost) {
+        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        lists[w].push_back(c.second); load[w] += c.first;
+    }
+    size_t slots = 0;
+    for (auto &l : lists) slots = std::max(slots, l.size());
+    // ---- words: weight pairs | lane descriptors | block descriptors | schedule ------------------------------
+    mb.seg.assign(2 * nwq + 32 * n_blocks + 2 * n_blocks + 1 + slots * warps, 0);
+    float *wq = reinterpret_cast<float *>(mb.seg.data());
+    int *lo_item = mb.seg.data() + 2 * nwq;
+    int *desc = lo_item + 32 * n_blocks;
+    int *sched = desc + 2 * n_blocks;
+    sched[0] = (int)slots;
+    for (size_t i = 0; i < slots * warps; ++i) sched[1 + i] = -1;
+    for (int w = 0; w < warps; ++w)
+        for (size_t i = 0; i < lists[w].size(); ++i) sched[1 + i * warps + w] = lists[w][i];
+    for (size_t b = 0; b < n_blocks; ++b) {
+        const Blk &B = blks[b];
+        for (int u = 0; u < U; ++u) {
+            const size_t sg = b * outs + u;
+            const int f = sg < S ? first[sg] : limit - 1, c = sg < S ? len[sg] : 0, q = B.q[u];
+            const int filt = (u < outs && sg < n_mel) ? (int)sg : 0xffff; // the last unit of a block only lends its D
+            for (int pl = 0; pl < P; ++pl) {
+                const size_t lane = (size_t)u * P + pl;
+                lo_item[b * 32 + lane] = (f + pl - q * P) | (filt << 16);
+                for (int j = 0; pl + j * P < c; ++j) {
+                    const size_t k = (size_t)f + pl + (size_t)j * P;
+                    const size_t at = 2 * ((size_t)B.off + 32 * (size_t)(j + q) + lane);
+                    wq[at] = sg < n_mel ? fb[k * n_mel + sg] : 0.0f;      // rising side of filter sg
+                    wq[at + 1] = sg >= 1 ? fb[k * n_mel + sg - 1] : 0.0f; // falling side of filter sg - 1
+                }
+            }
+        }
+        desc[2 * b] = B.off; desc[2 * b + 1] = B.nj;
+    }
+    mb.seg_nwq = (int)nwq; mb.seg_nblk = (int)n_blocks; mb.seg_log2p = lg; mb.seg_slots = (int)slots;
+    return true;
+}
+
 MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group,
-                        size_t stage_capacity_floats)
+                        size_t stage_capacity_floats, int vec)
 {
     MelBands mb;
     mb.lo.resize(n_mel); mb.cnt.resize(n_mel); mb.off.resize(n_mel);
@@ -243,71 +384,7 @@ MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int thread
     mb.sched[0] = (int)slots; mb.sched[1] = (int)nnz; mb.sched[2] = staged ? 1 : 0; mb.sched[3] = 0;
     for (int w = 0; w < warps; ++w)
         for (size_t i = 0; i < lists[w].size(); ++i) mb.sched[4 + i * warps + w] = lists[w][i];
-    // block-padded, tap-major copy (see MelBands::packed)
-    {
-        // Lane order and window shifts inside a block.  At every tap the 8 lanes of a 128-bit shared-memory phase
-        // read the slots (first bin + tap) of their filters; they collide when those are equal mod 8 -- which
-        // neighbouring mel filters are whenever their spacing is even (4-way at 12 bins, 8-way at 8).  All items of
-        // a block run the same number of taps, so (1) the filters (units of P adjacent lanes) may sit in any order
-        // and (2) a filter's window may start q P bins early, its first q taps being zeros: each phase is filled
-        // greedily with the (unit, shift) whose residues are still free.
-        const int unit_lanes = std::min(P, 32), units_per_block = 32 / unit_lanes;
-        const int units_per_phase = std::max(1, 8 / unit_lanes);
-        int max_shift = 2; // 3 and more cut the conflicts further but the longer bank no longer fits next to a 32-frame tile
-        if (const char *e = getenv("SGX_MEL_SHIFT")) max_shift = atoi(e);
-        struct Place { int m, q; };
-        std::vector<std::vector<Place>> placed(n_blocks);
-        std::vector<int> off(n_blocks), nj4(n_blocks);
-        size_t nwb = 0;
-        for (size_t b = 0; b < n_blocks; ++b) {
-            std::vector<int> pending; // filters of this block
-            for (int u = 0; u < units_per_block; ++u) {
-                const size_t m = (b * 32) / P + u;
-                if (m < n_mel) pending.push_back((int)m);
-            }
-            auto residues = [&](int m, int q) {
-                unsigned r = 0;
-                for (int pl = 0; pl < std::min(unit_lanes, 8); ++pl) r |= 1u << ((mb.lo[m] + pl - q * P) & 7);
-                return r;
-            };
-            int longest = 0;
-            while (!pending.empty()) {
-                unsigned occ = 0; // residues mod 8 taken in the phase being filled
-                for (int k = 0; k < units_per_phase && !pending.empty(); ++k) {
-                    size_t best_i = 0; int best_q = 0, best_cost = 1 << 30;
-                    for (size_t i = 0; i < pending.size(); ++i)
-                        for (int q = 0; q <= max_shift && q * P <= mb.lo[pending[i]]; ++q) {
-                            const int cost = __builtin_popcount(residues(pending[i], q) & occ) * 16 + q;
-                            if (cost < best_cost) { best_cost = cost; best_i = i; best_q = q; }
-                        }
-                    const int m = pending[best_i];
-                    occ |= residues(m, best_q);
-                    placed[b].push_back(Place{m, best_q});
-                    longest = std::max(longest, (mb.cnt[m] + P - 1) / P + best_q);
-                    pending.erase(pending.begin() + (long)best_i);
-                }
-            }
-            off[b] = (int)nwb; nj4[b] = std::max(4, (longest + 3) & ~3);
-            nwb += (size_t)32 * nj4[b];
-        }
-        mb.packed.assign(nwb + 32 * n_blocks + 2 * n_blocks, 0);
-        float *wb = reinterpret_cast<float *>(mb.packed.data());
-        int *lo_item = mb.packed.data() + nwb;
-        int *desc = lo_item + 32 * n_blocks;
-        for (size_t b = 0; b < n_blocks; ++b) {
-            for (int lane = 0; lane < 32; ++lane) lo_item[b * 32 + lane] = (int)(0xffffu << 16); // no filter: nothing is stored
-            for (size_t u = 0; u < placed[b].size(); ++u) {
-                const int m = placed[b][u].m, q = placed[b][u].q, c = mb.cnt[m];
-                for (int pl = 0; pl < unit_lanes; ++pl) {
-                    const size_t lane = u * unit_lanes + pl;
-                    lo_item[b * 32 + lane] = (mb.lo[m] + pl - q * P) | (m << 16);
-                    for (int j = 0; pl + j * P < c; ++j) wb[off[b] + 32 * (j + q) + lane] = mb.w[mb.off[m] + pl + j * P];
-                }
-            }
-            desc[2 * b] = off[b]; desc[2 * b + 1] = nj4[b];
-        }
-        mb.packed_nwb = (int)nwb; mb.packed_nblk = (int)n_blocks;
-    }
+    build_mel_segments(mb, fb, n_freq, n_mel, warps, vec);
     return mb;
 }
 

@@ -41,16 +41,18 @@ struct MelBands {
     int max_cnt = 0;
     int log2_split = 0;            // lanes cooperating on one filter (power of two <= 32)
     std::vector<int> sched;        // {slots, taps, staged, 0, block ids [slots][warps]}: balanced block lists per warp
-    // Block-padded copy of the bank for the kernels whose last FFT pass is fused with the split (they keep the
-    // magnitudes unpadded).  32-bit words: taps [sum_b 32 * nj4_b] (block b, tap j of work item i at
-    // off_b + 32 j + i, zero beyond an item's own taps; nj4_b = longest item of the block rounded up to 4),
-    // {first bin | filter << 16} per lane [32 * n_blocks] (0xffff: no filter), then {off_b, nj4_b} per block.  The P lanes
-    // of a filter are adjacent; the filters of a block are ordered so that the lanes of a shared-memory phase hit
-    // different bank groups.
-    std::vector<int> packed;
-    int packed_nwb = 0, packed_nblk = 0;
+    // Segment form of the bank for the kernels that keep the magnitudes unpadded (fused last pass, warp kernel); see
+    // build_mel_segments in host_tables.cpp.  32-bit words: weight pairs {rising, falling} [2 * 32 * sum_b nj_b]
+    // (block b, tap j of lane i at 2 * (off_b + 32 j + i), zero outside the lane's own bins), {first bin | filter << 16}
+    // per lane [32 * n_blocks] (0xffff: the lane produces no output), {off_b, nj_b} per block, then the schedule
+    // {slots, block ids [slots][warps]}.  Block b walks segments b (U - 1) ... b (U - 1) + U - 1 with U = 32 / P units of
+    // P adjacent lanes; unit u < U - 1 outputs filter b (U - 1) + u = U_u + D_(u+1).  Empty when the bank is not mel-like.
+    std::vector<int> seg;
+    int seg_nwq = 0, seg_nblk = 0, seg_log2p = 0, seg_slots = 0;
+    int seg_words(int warps) const { return 2 * seg_nwq + 34 * seg_nblk + 1 + seg_slots * warps; }
 };
+// `vec`: frames a thread group transforms together (magnitudes sit in shared memory as vectors of `vec` floats).
 MelBands make_mel_bands(const float *fb, size_t n_freq, size_t n_mel, int threads_per_group,
-                        size_t stage_capacity_floats);
+                        size_t stage_capacity_floats, int vec);
 
 } // namespace sgx

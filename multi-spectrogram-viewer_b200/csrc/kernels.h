@@ -33,11 +33,13 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &launch, cudaStr
 // 4 per filter for its descriptor), 0 when not a mel launch; the planner reports whether it got its own region.
 struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; int sample_floats; int warp2; };
 // `sample_floats`: 2 when the launch holds f32 stereo tracks (their tiles are staged as raw interleaved pairs), else 1.
-StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats = 0, int sample_floats = 1);
+// `warp2_ok`: every mel track of the launch has a segment-form bank (the warp kernel has no other mel path).
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats = 0, int sample_floats = 1, bool warp2_ok = true);
 
 // the warp-per-frame-pair kernel (n_fft = 2048); `launch.warp2` routes launch_stft here
 cudaError_t launch_stft_warp2(const StftLaunch &launch, cudaStream_t stream);
-size_t stft_warp2_fixed_smem(int bank_floats); // shared memory besides the PCM tile
+size_t stft_warp2_fixed_smem(int bank_floats, int warps); // shared memory besides the PCM tile
+int stft_warp2_warps();                                    // warps per CTA (8 unless SGX_W2_WARPS = 10 | 12)
 
 // FFT twiddle tables for one size (host vectors -> caller uploads).
 void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);
@@ -46,11 +48,11 @@ void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);
 cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s);
 // resets the range slot of every track of a K1 descriptor array to the identity of the reduce
 cudaError_t launch_range_reset(const StftTrack *descs, int n, cudaStream_t s);
-// reduces slots [n][2] -> local {max, -min}
-cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *local_max_negmin,
-                                cudaStream_t s);
-// {max, -min} -> state {max_db, min_db, changed}: the clamps of lib.rs:208-209 and the sticky
-// 1e-3 change detection of lib.rs:210-218, all on the device
+// reduces slots [n][2] -> local {max, -min, max_sr, max_sec} (the last two are host metadata passed through)
+cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *local_max_negmin, float max_sr,
+                                float max_sec, cudaStream_t s);
+// {max, -min, max_sr, max_sec} -> state {max_db, min_db, changed, max_sr, max_sec}: the clamps of lib.rs:208-209
+// and the sticky 1e-3 change detection of lib.rs:210-218, all on the device
 cudaError_t launch_range_commit(const float *max_negmin, float db_range, float *state,
                                 cudaStream_t s);
 

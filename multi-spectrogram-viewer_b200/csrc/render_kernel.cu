@@ -42,7 +42,7 @@ __global__ void range_reset_kernel(const StftTrack *__restrict__ descs, int n)
     }
 }
 
-__global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, float *out)
+__global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, float *out, float max_sr, float max_sec)
 {
     __shared__ float smax[32], smin[32];
     float mx = -INFINITY, mn = INFINITY;
@@ -58,8 +58,10 @@ __global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, f
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)blockDim.x / 32; ++w) { mx = fmaxf(mx, smax[w]); mn = fminf(mn, smin[w]); }
-        out[0] = mx;  // all-reduce(MAX) friendly pair {max, -min}
+        out[0] = mx;  // all-reduce(MAX) friendly: {max, -min, max sample rate, longest track in seconds}
         out[1] = -mn;
+        out[2] = max_sr;  // lib.rs:220-224 and lib.rs:178-182: metadata of this handle's tracks, so that one
+        out[3] = max_sec; // exchange serves everything update_spec_greys needs from the other shards
     }
 }
 
@@ -78,6 +80,7 @@ __global__ void range_commit_kernel(const float *__restrict__ max_negmin, float 
     // lib.rs:210-218: the stored range only moves when it differs by more than 1e-3
     if (abs_diff_ne(state[0], mx, 1e-3f)) { state[0] = mx; state[2] = 1.0f; }
     if (abs_diff_ne(state[1], mn, 1e-3f)) { state[1] = mn; state[2] = 1.0f; }
+    state[3] = max_negmin[2]; state[4] = max_negmin[3]; // max_sr, max_sec over all shards
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -790,9 +793,9 @@ cudaError_t launch_range_reset(const StftTrack *descs, int n, cudaStream_t s)
     count_launch();
     return cudaGetLastError();
 }
-cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *out, cudaStream_t s)
+cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *out, float max_sr, float max_sec, cudaStream_t s)
 {
-    range_reduce_kernel<<<1, 256, 0, s>>>(slots, n_slots, out);
+    range_reduce_kernel<<<1, 256, 0, s>>>(slots, n_slots, out, max_sr, max_sec);
     count_launch();
     return cudaGetLastError();
 }

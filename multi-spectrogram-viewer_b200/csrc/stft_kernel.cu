@@ -291,17 +291,17 @@ stft_db_kernel(const StftLaunch L)
     (void)T;
 
     // ---- filterbank of this track into its dedicated region (once per CTA and track) ----------------
-    // melp: the block-padded copy is used (fused kernels, magnitudes unpadded); else the banded copy, in the
+    // melp: the segment form of the bank is used (fused kernels, magnitudes unpadded); else the banded copy, in the
     // region when it fits, staged per round in the imaginary plane or read through L1 otherwise
     constexpr int RL_K = last_radix(H, PTS);
     constexpr bool FUSED_K = (PTS / RL_K) >= 2;
-    const bool melp = MEL && FUSED_K && td->melp != nullptr && td->melp_nwb + 34 * td->melp_nblk <= L.bank_floats;
+    const bool melp = MEL && FUSED_K && td->segp != nullptr && td->seg_words <= L.bank_floats;
     const bool bank_fits = MEL && (melp || ((__ldg(td->mel_cnt + 1) + 3) & ~3) + 4 * n_out <= L.bank_floats);
     if (MEL && bank_fits && td->mel_w != bank_src) {
         __syncthreads(); // other groups may still be projecting frames of the previous track
         if (melp) {
-            const int words = td->melp_nwb + 34 * td->melp_nblk;
-            const int *__restrict__ srcw = td->melp;
+            const int words = td->seg_words;
+            const int *__restrict__ srcw = td->segp;
             int *dstw = reinterpret_cast<int *>(bank);
             for (int i = tid; i < words; i += THREADS) dstw[i] = __ldg(srcw + i);
         } else {
@@ -626,49 +626,54 @@ stft_db_kernel(const StftLaunch L)
         // The filterbank taps and descriptors are first staged in the imaginary plane of the exchange
         // buffer -- it is dead once the spectrum has been read -- so the tap loop only touches shared memory.
         if (MEL && melp) {
-            // Block-padded bank: work item i of block b reads taps wb[off_b + 32 j + lane] (zeros beyond its own)
-            // and the unpadded magnitudes of bins bin0 + j P -- no predicates, no index arithmetic beyond one
-            // add per tap; nj4_b taps for the whole block.
+            // Segment form of the bank (host_tables.h MelBands::seg): a lane walks the bins of ONE segment, reads each
+            // magnitude vector once and feeds two accumulators -- U (rising side, filter s) and D (falling side, filter
+            // s - 1); filter m = U_m + D_(m+1), the neighbour's D arriving by one shuffle.  Taps are block-padded and
+            // tap-major: no predicates, one 64-bit and one vector shared load per tap.
             constexpr int NWARPS = NT / 32;
-            const int *__restrict__ sched = td->mel_cnt;
-            const int nslots = __ldg(sched);
-            const int lg = td->mel_log2p, P = 1 << lg;
-            const int nwb = td->melp_nwb, nblk = td->melp_nblk;
-            const float *wb = bank;
-            const int *lo_s = reinterpret_cast<const int *>(bank) + nwb;
+            const int lg = td->seg_log2p, P = 1 << lg;
+            const int nwq = td->seg_nwq, nblk = td->seg_nblk;
+            const float2 *wq = reinterpret_cast<const float2 *>(bank);
+            const int *lo_s = reinterpret_cast<const int *>(bank) + 2 * nwq;
             const int2 *desc_s = reinterpret_cast<const int2 *>(lo_s + 32 * nblk);
+            const int *sched = lo_s + 34 * nblk; // {slots, block ids [slots][NWARPS]}
             group_sync<G, NT>(grp); // magnitudes of all bins are in the buffer
             const int wg = gt >> 5, lane = gt & 31;
             const int stride = V << lg;
+            const int nslots = sched[0];
             for (int slot = 0; slot < nslots; ++slot) {
-                const int blk = __ldg(sched + 4 + slot * NWARPS + wg); // warp-uniform
+                const int blk = sched[1 + slot * NWARPS + wg]; // warp-uniform
                 if (blk < 0) continue;
                 const int2 bd = desc_s[blk];
                 const int li = lo_s[blk * 32 + lane];   // first bin | filter << 16
                 const int m = (int)((unsigned)li >> 16), pl = lane & (P - 1);
-                const float *wp = wb + bd.x + lane;
+                const float2 *wp = wq + bd.x + lane;
                 const float *mp = sre + (li & 0xffff) * V;
-                pk accp[VP];
+                pk up[VP], dn[VP];
 #pragma unroll
-                for (int v = 0; v < VP; ++v) accp[v] = make_float2(0.0f, 0.0f);
-                for (int j4 = 0; j4 < bd.y; j4 += 4) {
+                for (int v = 0; v < VP; ++v) { up[v] = make_float2(0.0f, 0.0f); dn[v] = make_float2(0.0f, 0.0f); }
+                for (int j2 = 0; j2 < bd.y; j2 += 2) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float wgt = wp[(j4 + u) * 32];
+                    for (int u = 0; u < 2; ++u) {
+                        const float2 wgt = wp[(j2 + u) * 32];
                         pk mg[VP];
                         ld_vec<VP>(mp, mg);
                         mp += stride;
 #pragma unroll
-                        for (int v = 0; v < VP; ++v) accp[v] = pk_fmas(mg[v], wgt, accp[v]);
+                        for (int v = 0; v < VP; ++v) { up[v] = pk_fmas(mg[v], wgt.x, up[v]); dn[v] = pk_fmas(mg[v], wgt.y, dn[v]); }
                     }
                 }
                 float acc[V];
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc[v] = pk_get<VP>(accp, v);
-                for (int sh = P >> 1; sh > 0; sh >>= 1)
-#pragma unroll
-                    for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], sh);
-                if (m < n_out && pl == 0) {
+                for (int v = 0; v < V; ++v) {
+                    float a = pk_get<VP>(up, v), d = pk_get<VP>(dn, v);
+                    for (int sh = P >> 1; sh > 0; sh >>= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, sh);
+                        d += __shfl_xor_sync(0xffffffffu, d, sh);
+                    }
+                    acc[v] = a + __shfl_down_sync(0xffffffffu, d, P); // D of the next segment
+                }
+                if (m != 0xffff && pl == 0) {
                     // Frames beyond the tile's last one were computed from a copy of that last frame (the clamp in
                     // the first pass), so their dB values may enter the extrema; only the store is predicated.
                     float *op = out + (size_t)(t0 + fl0) * n_out + m;
@@ -972,15 +977,16 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
     }
     SGX_K1_TABLE(X)
 #undef X
-    // n_fft = 2048: the warp-per-frame-pair kernel is the default (SGX_K1W2=0 keeps the block kernel)
-    static const bool w2_off = getenv("SGX_K1W2") && atoi(getenv("SGX_K1W2")) == 0;
-    cfg->warp2 = h == 1024 && !cfg->generic && cfg->fused && !w2_off && want_pts == 0;
+    // n_fft = 2048: SGX_K1W2=1 selects the warp-per-frame-pair kernel (stft_warp2_kernel.cu; measured 6.42 vs 6.32 ms
+    // per C5 step, see its header) -- an evaluated alternative, off by default
+    static const bool w2_on = getenv("SGX_K1W2") && atoi(getenv("SGX_K1W2")) == 1;
+    cfg->warp2 = h == 1024 && !cfg->generic && cfg->fused && w2_on && want_pts == 0;
     return true;
 }
 
 size_t stft_max_dynamic_smem() { return 227 * 1024; }
 
-StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, int sample_floats)
+StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, int sample_floats, bool warp2_ok)
 {
     StftTiling t{};
     if (cfg.generic) {
@@ -990,18 +996,19 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, 
     }
     int want_nfr = 0;
     if (const char *e = getenv("SGX_K1_NFR")) want_nfr = atoi(e);
-    if (cfg.warp2) {
+    if (cfg.warp2 && warp2_ok) {
         // eight warps x two frames per round; the tile gets what the exchange planes, tables and filterbank leave
-        const size_t fixed = stft_warp2_fixed_smem(bank_floats);
+        const int nw = stft_warp2_warps();
+        const size_t fixed = stft_warp2_fixed_smem(bank_floats, nw);
         const long cap_floats = stft_max_dynamic_smem() > fixed ? (long)((stft_max_dynamic_smem() - fixed) / sizeof(float)) : 0;
         int best = 0;
         for (int mult = 1; mult <= 4; ++mult) {
-            const int nfr = 16 * mult;
+            const int nfr = 2 * nw * mult;
             const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
-            if (need <= cap_floats && (nfr <= (want_nfr ? want_nfr : 32) || best == 0)) best = nfr;
+            if (need <= cap_floats && (nfr <= (want_nfr ? want_nfr : 6 * nw) || best == 0)) best = nfr;
         }
         if (best > 0) {
-            t.frames_per_tile = best; t.staged = 1; t.warp2 = 1; t.bank_floats = bank_floats; t.sample_floats = 1;
+            t.frames_per_tile = best; t.staged = 1; t.warp2 = nw; t.bank_floats = bank_floats; t.sample_floats = 1;
             t.tile_floats = (int)((3 + (long)(best - 1) * max_hop + cfg.n_fft + 3) & ~3L) + 4;
             t.smem_bytes = fixed + (size_t)t.tile_floats * sizeof(float);
             return t;

@@ -12,7 +12,15 @@
 //     the bin pairs (k, h - k) of its 16 lowest bins, so the split costs 32 shuffles per frame and no loads.
 // No block barrier sits on the frame path; the eight warps of a CTA only meet at the PCM tile, which is staged by
 // TMA exactly as in the block kernel (bulk copy + mbarrier, next tile prefetched by the last warp to consume this one).
+//
+// MEASURED (B200, C5, K1 ms per step; profiles/r02_k1_w2_*): 535 shared-memory wavefronts per frame instead of 715 and
+// 1,670 instead of 2,000 instructions, yet 6.42 ms against the block kernel's 6.32: 128 data registers per thread leave
+// 8 warps per SM (2 per scheduler), and a packed FADD2 / FFMA2 holds its warp for two issue cycles, so the kernel is
+// bound by per-warp latency (issue slots 44 % busy, shared-memory pipe 51 %) where the block kernel, with 16 warps, is
+// bound by the shared-memory pipe (72 %).  10 and 12 warps (168 registers, a few spills) are no faster (8.0 / 7.1 ms).
+// Kept as a parity-tested alternative (SGX_K1W2=1); the block kernel stays the default at every FFT size.
 #include <cstdint>
+#include <cstdlib>
 #include <algorithm>
 
 #include "device_common.cuh"
@@ -24,15 +32,14 @@ namespace sgx {
 namespace {
 
 constexpr int kW2H = 1024;                  // complex points
-constexpr int kW2Warps = 8;
-constexpr int kW2Threads = kW2Warps * 32;
+constexpr int kW2MaxWarps = 12;             // 8 by default; 10 / 12 trade registers per thread for resident warps (SGX_W2_WARPS)
 constexpr int kW2Pitch = 33;                // float2 elements per row of a warp's exchange plane (conflict-free both ways)
 constexpr int kW2Plane = 32 * kW2Pitch;     // 8448 bytes; also holds the 1025 magnitude pairs of the two frames
 
-template <bool MEL>
-__global__ void __launch_bounds__(kW2Threads, 1) stft_warp2_kernel(const StftLaunch L)
+template <bool MEL, int kW2Warps>
+__global__ void __launch_bounds__(kW2Warps * 32, 1) stft_warp2_kernel(const StftLaunch L)
 {
-    constexpr int H = kW2H, F = 2 * kW2H;
+    constexpr int H = kW2H, F = 2 * kW2H, kW2Threads = kW2Warps * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned *done_cnt = reinterpret_cast<unsigned *>(smem_raw + 8); // warps that have consumed the current tile
@@ -115,8 +122,8 @@ __global__ void __launch_bounds__(kW2Threads, 1) stft_warp2_kernel(const StftLau
             const float2 *__restrict__ wsrc = reinterpret_cast<const float2 *>(td->win_f);
             for (int i = tid; i < H; i += kW2Threads) win_s[i] = __ldg(wsrc + i);
             if (MEL) {
-                const int words = td->melp_nwb + 34 * td->melp_nblk;
-                const int *__restrict__ srcw = td->melp;
+                const int words = td->seg_words;
+                const int *__restrict__ srcw = td->segp;
                 int *dstw = reinterpret_cast<int *>(bank);
                 for (int i = tid; i < words; i += kW2Threads) dstw[i] = __ldg(srcw + i);
             }
@@ -274,41 +281,49 @@ __global__ void __launch_bounds__(kW2Threads, 1) stft_warp2_kernel(const StftLau
             }
             if (l0) emit(H / 2, re[16][0], pk_neg(im[16][0])); // X[h/2] = conj(Z[h/2])
 
-            // ---- F: banded mel projection + dB (block-padded bank, see MelBands::packed) ----------------------------
+            // ---- F: mel projection + dB, segment form of the bank (host_tables.h MelBands::seg) ----------------------
+            // A lane walks the bins of ONE segment: every magnitude pair is read once and feeds U (rising side, filter s)
+            // and D (falling side, filter s - 1); filter m = U_m + D_(m+1), the neighbour's D arriving by a shuffle.
             if (MEL) {
                 __syncwarp(); // magnitudes of all bins are in the plane
-                const int lg = td->mel_log2p, P = 1 << lg;
-                const int nwb = td->melp_nwb, nblk = td->melp_nblk;
-                const float *wb = bank;
-                const int *lo_s = reinterpret_cast<const int *>(bank) + nwb;
+                const int lg = td->seg_log2p, P = 1 << lg;
+                const int nwq = td->seg_nwq, nblk = td->seg_nblk;
+                const float2 *wq = reinterpret_cast<const float2 *>(bank);
+                const int *lo_s = reinterpret_cast<const int *>(bank) + 2 * nwq;
                 const int2 *desc_s = reinterpret_cast<const int2 *>(lo_s + 32 * nblk);
-                const int stride = 1 << lg;
+                const int plm = lane & (P - 1);
+                float *orow = out + (size_t)(t0 + fl0) * n_out;
+                const bool two = fl0 + 1 < nfr;
                 for (int blk = 0; blk < nblk; ++blk) {
                     const int2 bd = desc_s[blk];
                     const int li = lo_s[blk * 32 + lane];   // first bin | filter << 16
-                    const int m = (int)((unsigned)li >> 16), plm = lane & (P - 1);
-                    const float *wp = wb + bd.x + lane;
+                    const int m = (int)((unsigned)li >> 16);
+                    const float2 *wp = wq + bd.x + lane;
                     const float2 *mp = magbuf + (li & 0xffff);
-                    pk acc = make_float2(0.0f, 0.0f);
-                    for (int j4 = 0; j4 < bd.y; j4 += 4) {
+                    pk up = make_float2(0.0f, 0.0f), dn = up;
+                    for (int j2 = 0; j2 < bd.y; j2 += 2) { // (fully unrolled tap bodies behind a switch were slower: 7.1 vs 6.4 ms)
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float wgt = wp[(j4 + u) * 32];
+                        for (int u = 0; u < 2; ++u) {
+                            const float2 wgt = wp[(j2 + u) * 32];
                             const pk mg = *mp;
-                            mp += stride;
-                            acc = pk_fmas(mg, wgt, acc);
+                            mp += P;
+                            up = pk_fmas(mg, wgt.x, up); dn = pk_fmas(mg, wgt.y, dn);
                         }
                     }
-                    for (int sh = P >> 1; sh > 0; sh >>= 1) {
-                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh);
-                        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
+                    if (P > 1) {
+                        for (int sh = P >> 1; sh > 0; sh >>= 1) {
+                            up.x += __shfl_xor_sync(0xffffffffu, up.x, sh); up.y += __shfl_xor_sync(0xffffffffu, up.y, sh);
+                            dn.x += __shfl_xor_sync(0xffffffffu, dn.x, sh); dn.y += __shfl_xor_sync(0xffffffffu, dn.y, sh);
+                        }
                     }
-                    if (m < n_out && plm == 0) {
-                        const float y0 = amp_to_db_dev(acc.x), y1 = amp_to_db_dev(acc.y); // decibel.rs:33-88
+                    const float a0 = up.x + __shfl_down_sync(0xffffffffu, dn.x, P); // D of the next segment
+                    const float a1 = up.y + __shfl_down_sync(0xffffffffu, dn.y, P);
+                    if (m != 0xffff && plm == 0) {
+                        const float y0 = amp_to_db_dev(a0), y1 = amp_to_db_dev(a1); // decibel.rs:33-88
                         vmax = fmaxf(vmax, fmaxf(y0, y1)); vmin = fminf(vmin, fminf(y0, y1));
-                        float *op = out + (size_t)(t0 + fl0) * n_out + m;
+                        float *op = orow + m;
                         op[0] = y0;
-                        if (fl0 + 1 < nfr) op[n_out] = y1;
+                        if (two) op[n_out] = y1;
                     }
                 }
             }
@@ -320,32 +335,50 @@ __global__ void __launch_bounds__(kW2Threads, 1) stft_warp2_kernel(const StftLau
 
 } // namespace
 
-size_t stft_warp2_fixed_smem(int bank_floats)
+size_t stft_warp2_fixed_smem(int bank_floats, int warps)
 {
-    return 16 + (size_t)kW2Warps * kW2Plane * sizeof(float2) + (size_t)(kW2H + kW2H + kW2H / 2) * sizeof(float2) +
+    return 16 + (size_t)warps * kW2Plane * sizeof(float2) + (size_t)(kW2H + kW2H + kW2H / 2) * sizeof(float2) +
            (size_t)bank_floats * sizeof(float);
 }
 
+int stft_warp2_warps()
+{
+    static const int w = [] {
+        const char *e = getenv("SGX_W2_WARPS");
+        const int v = e ? atoi(e) : 8;
+        return (v == 10 || v == 12) ? v : 8;
+    }();
+    return w;
+}
+
+namespace {
+template <bool MEL, int NW> cudaError_t launch_w2(const StftLaunch &L, size_t smem, int grid, cudaStream_t stream)
+{
+    auto kern = stft_warp2_kernel<MEL, NW>;
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NW * 32, smem, stream>>>(L);
+    count_launch();
+    return cudaGetLastError();
+}
+} // namespace
+
 cudaError_t launch_stft_warp2(const StftLaunch &L, cudaStream_t stream)
 {
-    const size_t smem = stft_warp2_fixed_smem(L.bank_floats) + (size_t)L.tile_floats * sizeof(float);
+    const int nw = L.warp2;
+    const size_t smem = stft_warp2_fixed_smem(L.bank_floats, nw) + (size_t)L.tile_floats * sizeof(float);
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
     const int grid = std::min(L.n_tiles, sms);
-    cudaError_t e;
-    if (L.mode == MODE_MEL_DB) {
-        e = ensure_dynamic_smem(reinterpret_cast<const void *>(stft_warp2_kernel<true>), smem);
-        if (e != cudaSuccess) return e;
-        stft_warp2_kernel<true><<<grid, kW2Threads, smem, stream>>>(L);
-    } else {
-        e = ensure_dynamic_smem(reinterpret_cast<const void *>(stft_warp2_kernel<false>), smem);
-        if (e != cudaSuccess) return e;
-        stft_warp2_kernel<false><<<grid, kW2Threads, smem, stream>>>(L);
+    const bool mel = L.mode == MODE_MEL_DB;
+    switch (nw) {
+    case 8: return mel ? launch_w2<true, 8>(L, smem, grid, stream) : launch_w2<false, 8>(L, smem, grid, stream);
+    case 10: return mel ? launch_w2<true, 10>(L, smem, grid, stream) : launch_w2<false, 10>(L, smem, grid, stream);
+    case 12: return mel ? launch_w2<true, 12>(L, smem, grid, stream) : launch_w2<false, 12>(L, smem, grid, stream);
     }
-    count_launch();
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 } // namespace sgx

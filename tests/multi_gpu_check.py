@@ -26,7 +26,8 @@ def main():
     tracks = [synth.derive_track(synth.base_clip(4 * sr + 321, sr, seed=100 + sr), t) for t, sr in enumerate(srs)]
     mine = msv.shard_ids(n_tracks, world, rank)
     dev = [torch.from_numpy(tracks[t]).cuda() for t in mine]
-    sm = msv.ShardedMultiTrack(device=local)
+    sm = msv.ShardedMultiTrack(device=local)   # attaches this rank's handle to the library's NCCL communicator
+    assert sm.mt.device_count() == (1, rank, world)
     sm.add_tracks_device(mine, [d.data_ptr() for d in dev], [d.numel() for d in dev], [srs[t] for t in mine], keepalive=dev)
     outs = []
     for t in mine:
@@ -46,6 +47,30 @@ def main():
         ok = ok and same
         print(f"rank {rank}: track {t} sr={srs[t]} pixels identical to single-process: {same}", flush=True)
     print(f"rank {rank}: range sharded {got_range} single {want_range}", flush=True)
+    # metadata of the other shards arrived with the range: max_sec over ALL tracks, not just this rank's
+    ok = ok and abs(sm.mt.get_max_sec() - ref.get_max_sec()) < 1e-6
+    # the whole-batch form of the call: every rank passes all ids, the library keeps its share; host PCM, host images
+    hm = msv.MultiTrack(device=local)
+    hm.attach_nccl(msv.sharded.broadcast_unique_id(device=f"cuda:{local}"), rank, world)
+    hm.add_tracks_pcm(list(range(n_tracks)), [tracks[t] if t % world == rank else None for t in range(n_tracks)], srs)
+    imgs = hm.get_spec_images(mine, 100.0, 300, 4)
+    for t, im in zip(mine, imgs):
+        same = np.array_equal(im, ref.get_spec_image_rgba(t, 100.0, 300))
+        ok = ok and same
+        print(f"rank {rank}: track {t} whole-batch call + batched host images identical: {same}", flush=True)
+    # removing the loudest track re-normalises every rank (lib.rs:265-292): collective remove
+    loud = int(np.argmax([float(np.abs(x).max()) for x in tracks]))
+    hm.remove_track(loud)
+    ref2 = msv.MultiTrack(device=local)
+    keep = [t for t in range(n_tracks) if t != loud]
+    ref2.add_tracks_pcm(keep, [tracks[t] for t in keep], [srs[t] for t in keep])
+    same = (hm.get_max_db(), hm.get_min_db()) == (ref2.get_max_db(), ref2.get_min_db())
+    for t in mine:
+        if t != loud:
+            same = same and np.array_equal(hm.get_spec_image(t, 100.0, 300), ref2.get_spec_image(t, 100.0, 300))
+    print(f"rank {rank}: after the collective remove of track {loud}: identical to single-process: {same}", flush=True)
+    ok = ok and same
+    hm.close(); ref2.close()
     # ---- n3: ONE long track time-sharded over all ranks (strips of columns) -----------------------------------
     sr2 = 48000
     long_track = synth.base_clip(90 * sr2 + 123, sr2, seed=4242)

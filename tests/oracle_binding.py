@@ -258,8 +258,9 @@ class Oracle:
 
     # ---- whole pipeline (MultiTrack::add_tracks + get_spec_image for all tracks) ---------------
     def pipeline(self, wavs, srs, params, windows, mel_fbs, mel_scale=True, db_range=120.0, px_per_sec=100.0, nheight=500,
-                 channels=3, dense_mel=False, parallel_render=True, render=True):
-        """wavs: list of mono f32 arrays; params: list of (win, hop, n_fft); returns (images, max_db, min_db)."""
+                 channels=3, dense_mel=False, parallel_render=True, render=True, out_imgs=None):
+        """wavs: list of mono f32 arrays; params: list of (win, hop, n_fft); returns (images, max_db, min_db).
+        out_imgs: images of a previous call to write into (a timed loop then allocates nothing)."""
         n = len(wavs)
         wavs = [np.ascontiguousarray(w, np.float32) for w in wavs]
         windows = [np.ascontiguousarray(w, np.float32) for w in windows]
@@ -267,10 +268,11 @@ class Oracle:
         PP = _vp * n
         SZ = _sz * n
         U32 = _u32 * n
-        imgs = []
-        for w, sr in zip(wavs, srs):
-            nw = self.calc_nwidth(px_per_sec, w.size, sr)
-            imgs.append(np.zeros((nheight, nw, channels), np.uint8))
+        imgs = [] if out_imgs is None else out_imgs
+        if out_imgs is None:
+            for w, sr in zip(wavs, srs):
+                nw = self.calc_nwidth(px_per_sec, w.size, sr)
+                imgs.append(np.zeros((nheight, nw, channels), np.uint8))
         a, b = _f(), _f()
         use_mel = any(f is not None for f in fbs)
         self.lib.orc_pipeline.argtypes = [_sz, PP, SZ, U32, SZ, SZ, SZ, PP, _vp, _vp, C.c_int, _f, _f, _u32, C.c_int, C.c_int,

@@ -125,10 +125,10 @@ def test_many_zoom_levels_do_not_invalidate_axis_tables(msv):
         fresh.close()
 
 
-def test_block_kernel_at_n_fft_2048_parity(orc):
-    """n_fft = 2048 has two kernels: the warp-per-frame-pair one (default, exercised by every other test) and the
-    block kernel that serves the other FFT sizes (SGX_K1W2=0).  The block kernel must meet the same tolerances at
-    2048 too; the choice is made per process, so it runs in a child interpreter."""
+def test_warp_pair_kernel_at_n_fft_2048_parity(orc):
+    """n_fft = 2048 has two kernels: the block kernel (default, exercised by every other test) and the
+    warp-per-frame-pair one (SGX_K1W2=1, csrc/stft_warp2_kernel.cu).  The alternative must meet the same
+    tolerances; the choice is made per process, so it runs in a child interpreter."""
     import subprocess
     import sys
     import os
@@ -145,17 +145,17 @@ got = msv.perform_stft(x, 1920, 480, 2048)
 peak = np.abs(ref).max(axis=1, keepdims=True)
 assert (np.abs(got - ref) / peak).max() <= 1e-4
 fb = msv.calc_mel_fb_default(48000, 2048)
-assert_db_close(msv.melspectrogram_db(x, 1920, 480, 2048, None, fb), orc.calc_spec(x, 1920, 480, 2048, None, fb), "K1 block mel")
-assert_db_close(msv.melspectrogram_db(x, 2048, 512, 2048), orc.calc_spec(x, 2048, 512, 2048), "K1 block linear")
+assert_db_close(msv.melspectrogram_db(x, 1920, 480, 2048, None, fb), orc.calc_spec(x, 1920, 480, 2048, None, fb), "K1 W2 mel")
+assert_db_close(msv.melspectrogram_db(x, 2048, 512, 2048), orc.calc_spec(x, 2048, 512, 2048), "K1 W2 linear")
 y = synth.base_clip(2 * 44100, 44100, 6)  # odd hop 441: unaligned frame starts
 fb = msv.calc_mel_fb_default(44100, 2048)
-assert_db_close(msv.melspectrogram_db(y, 1764, 441, 2048, None, fb), orc.calc_spec(y, 1764, 441, 2048, None, fb), "K1 block 44.1k")
-print("K1 BLOCK OK")
+assert_db_close(msv.melspectrogram_db(y, 1764, 441, 2048, None, fb), orc.calc_spec(y, 1764, 441, 2048, None, fb), "K1 W2 44.1k")
+print("K1 W2 OK")
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SGX_K1W2="0")
+    env = dict(os.environ, SGX_K1W2="1")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "K1 BLOCK OK" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "K1 W2 OK" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("sr,seconds,px,settings_kw", [
