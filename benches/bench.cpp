@@ -72,6 +72,7 @@ static int bench_c5(int n_tracks, int seconds)
         for (size_t i = 0; i < n; ++i) tracks[(size_t)t][i] = base[i] * g;
     }
     for (int t = 0; t < n_tracks; ++t) { ids[(size_t)t] = (size_t)t; pcm[(size_t)t] = tracks[(size_t)(t % distinct)].data(); }
+    for (int t = 0; t < distinct; ++t) check(sgx_host_pin(tracks[(size_t)t].data(), n * sizeof(float)), "pin PCM");
     int changed = 0;
     using clk = std::chrono::steady_clock;
     check(sgx_mt_add_tracks_pcm(mt, ids.data(), ids.size(), pcm.data(), ns.data(), srs.data(), chs.data(), &changed), "add_tracks (warm-up)");
@@ -79,7 +80,10 @@ static int bench_c5(int n_tracks, int seconds)
     check(sgx_mt_get_spec_images(mt, ids.data(), ids.size(), 100.0f, 500, 4, nullptr, nullptr, need.data()), "image sizes");
     std::vector<std::vector<uint8_t>> imgs((size_t)n_tracks);
     std::vector<uint8_t *> outs((size_t)n_tracks);
-    for (int t = 0; t < n_tracks; ++t) { imgs[(size_t)t].resize(need[(size_t)t]); outs[(size_t)t] = imgs[(size_t)t].data(); }
+    for (int t = 0; t < n_tracks; ++t) {
+        imgs[(size_t)t].resize(need[(size_t)t]); outs[(size_t)t] = imgs[(size_t)t].data();
+        check(sgx_host_pin(outs[(size_t)t], need[(size_t)t]), "pin image");
+    }
     double best_add = 1e30, best_all = 1e30;
     for (int rep = 0; rep < 3; ++rep) {
         const auto t0 = clk::now();
@@ -93,10 +97,12 @@ static int bench_c5(int n_tracks, int seconds)
     float mx = 0, mn = 0;
     check(sgx_mt_get_max_db(mt, &mx), "max_db"); check(sgx_mt_get_min_db(mt, &mn), "min_db");
     const double audio_s = (double)n_tracks * seconds;
-    std::printf("%-28s %d tracks x %d s on %d GPU(s), pageable host buffers: add_tracks %.1f ms, + get_spec_images %.1f ms  "
+    std::printf("%-28s %d tracks x %d s on %d GPU(s), pinned host buffers: add_tracks %.1f ms, + get_spec_images %.1f ms  "
                 "(%.0f audio-s/s end to end)  range [%.2f, %.2f] dB  kernels launched %llu\n",
                 "add track x256 (all GPUs)", n_tracks, seconds, n_dev, best_add, best_all, audio_s / (best_all * 1e-3), mx, mn,
                 (unsigned long long)sgx_kernel_launch_count());
+    for (int t = 0; t < distinct; ++t) sgx_host_unpin(tracks[(size_t)t].data());
+    for (int t = 0; t < n_tracks; ++t) sgx_host_unpin(outs[(size_t)t]);
     sgx_mt_free(mt);
     return 0;
 }

@@ -61,6 +61,12 @@ SGX_API const char *sgx_last_error(void);
 SGX_API int sgx_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
                             size_t *total_mem);
 
+/* Page-locks (pins) an existing host allocation so that the uploads of sgx_mt_add_tracks_pcm* and the downloads of
+ * sgx_mt_get_spec_images* are true DMA transfers that overlap kernels and each other (pageable memory is staged
+ * through a driver buffer, several times slower).  A host written in Rust / C needs no CUDA binding for this. */
+SGX_API int sgx_host_pin(void *ptr, size_t bytes);
+SGX_API int sgx_host_unpin(void *ptr);
+
 /* Number of kernels this library has launched in the calling process (all handles). */
 SGX_API uint64_t sgx_kernel_launch_count(void);
 

@@ -71,6 +71,8 @@ PROTOTYPES = {
     "sgx_last_error": (C.c_char_p, []),
     "sgx_device_info": (C.c_int, [C.c_int, _pi, _pi, _pi, _psz]),
     "sgx_kernel_launch_count": (C.c_uint64, []),
+    "sgx_host_pin": (C.c_int, [_vp, _sz]),
+    "sgx_host_unpin": (C.c_int, [_vp]),
     "sgx_settings_default": (None, [C.POINTER(Settings)]),
     "sgx_mt_new": (C.c_int, [C.POINTER(_vp)]),
     "sgx_mt_new_ex": (C.c_int, [C.POINTER(Settings), C.c_int, _vp, C.POINTER(_vp)]),

@@ -45,8 +45,18 @@ struct sgx_multitrack {
     }
 };
 
+// Entry points may switch the CUDA device of the calling thread (a handle lives on its own device, a multi-device
+// handle walks several); the caller's current device is put back on the way out -- a host that also uses CUDA
+// (PyTorch does) must not find its "current device" changed by a call into this library.
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceRestore() { if (prev >= 0) { int now = -1; if (cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev); } }
+};
+
 template <class F> static int guarded(F &&f)
 {
+    DeviceRestore restore;
     try {
         f();
         return SGX_OK;
@@ -88,6 +98,18 @@ int sgx_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, siz
 }
 
 uint64_t sgx_kernel_launch_count(void) { return launch_count(); }
+
+int sgx_host_pin(void *ptr, size_t bytes)
+{
+    return guarded([&] {
+        REQUIRE(ptr && bytes, "NULL argument");
+        SGX_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    });
+}
+int sgx_host_unpin(void *ptr)
+{
+    return guarded([&] { REQUIRE(ptr, "NULL argument"); SGX_CUDA(cudaHostUnregister(ptr)); });
+}
 
 void sgx_settings_default(sgx_settings *s)
 {

@@ -85,6 +85,9 @@ FftPlan &DeviceCtx::plan(size_t n_fft)
         p->tw.alloc(h); p->split.alloc(h / 2 + 1);
         SGX_CUDA(cudaMemcpy(p->tw.p, tw.data(), sizeof(float2) * h, cudaMemcpyHostToDevice));
         SGX_CUDA(cudaMemcpy(p->split.p, sp.data(), sizeof(float2) * (h / 2 + 1), cudaMemcpyHostToDevice));
+        const std::vector<float2> pt = make_fft_pass_tables(h, p->cfg.pts);
+        p->twr.alloc(pt.size());
+        SGX_CUDA(cudaMemcpy(p->twr.p, pt.data(), sizeof(float2) * pt.size(), cudaMemcpyHostToDevice));
     }
     it = plans_.emplace(n_fft, std::move(p)).first;
     return *it->second;
@@ -427,7 +430,7 @@ void MultiTrack::analyse(const std::vector<size_t> &ids, std::vector<PcmSource> 
     for (size_t id : ids) by_fft[tracks_.at(id).n_fft].push_back(id);
     std::vector<StftTrack> descs;
     std::vector<size_t> desc_ids;
-    struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; };
+    struct Group { size_t n_fft; size_t first, count; StftTiling tiling; int n_tiles; bool raw_loader = false; };
     std::vector<Group> groups;
     for (auto &kv : by_fft) {
         const StftConfig &cfg = ctx_->plan(kv.first).cfg;
@@ -440,13 +443,15 @@ void MultiTrack::analyse(const std::vector<size_t> &ids, std::vector<PcmSource> 
                 bank_floats = std::max(bank_floats, tt.bank_floats(cfg.fused));
             }
         int sample_floats = 1; // f32 stereo tracks stage raw interleaved pairs: twice the room per sample
-        bool warp2_ok = true;
+        bool warp2_ok = true, raw_loader = false; // int16 mono tracks stage their 16-bit samples
         for (size_t id : kv.second) {
             const Track &t = tracks_.at(id);
-            if (set_.freq_scale == SGX_FREQ_MEL && t.ch == 2 && t.fmt == PCM_F32) sample_floats = 2;
+            if (t.ch == 2 && t.fmt == PCM_F32) sample_floats = 2;
+            if (t.ch == 1 && t.fmt == PCM_I16) raw_loader = true;
             if (set_.freq_scale == SGX_FREQ_MEL && t.tables->seg_nblk == 0) warp2_ok = false;
         }
         Group g{kv.first, descs.size(), 0, plan_stft_tiles(cfg, max_hop, bank_floats, sample_floats, warp2_ok), 0};
+        g.raw_loader = raw_loader;
         // a track id may appear twice in id_list; the last one wins, launch it once
         std::vector<size_t> uniq;
         for (size_t id : kv.second) if (std::find(uniq.begin(), uniq.end(), id) == uniq.end()) uniq.push_back(id);
@@ -472,8 +477,8 @@ void MultiTrack::analyse(const std::vector<size_t> &ids, std::vector<PcmSource> 
         L.tracks = d_stft_.p + g.first; L.n_tracks = (int)g.count; L.n_tiles = g.n_tiles;
         L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
         L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
-        L.tile_floats = g.tiling.tile_floats; L.bank_floats = g.tiling.bank_floats; L.tw = pl.tw.p; L.split = pl.split.p;
-        L.stereo_raw = g.tiling.sample_floats == 2 ? 1 : 0; L.warp2 = g.tiling.warp2;
+        L.tile_floats = g.tiling.tile_floats; L.bank_floats = g.tiling.bank_floats; L.tw = pl.tw.p; L.split = pl.split.p; L.twr = pl.twr.p;
+        L.stereo_raw = g.tiling.sample_floats == 2 ? 1 : (g.raw_loader ? 2 : 0); L.warp2 = g.tiling.warp2;
         if (!pipelined) { SGX_CUDA(launch_stft(pl.cfg, L, stream_)); continue; }
         for (size_t k = 0; k < g.count; ++k) {
             const size_t di = g.first + k;
@@ -831,7 +836,7 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     L.n_tiles = (int)(((size_t)T + tl.frames_per_tile - 1) / tl.frames_per_tile);
     L.mode = mode; L.frames_per_tile = tl.frames_per_tile; L.staged = tl.staged; L.tile_floats = tl.tile_floats;
     L.bank_floats = tl.bank_floats; L.warp2 = tl.warp2;
-    L.tw = pl.tw.p; L.split = pl.split.p;
+    L.tw = pl.tw.p; L.split = pl.split.p; L.twr = pl.twr.p;
     SGX_CUDA(launch_stft(pl.cfg, L, s));
     SGX_CUDA(cudaMemcpyAsync(out, d_out.p, elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     SGX_CUDA(cudaStreamSynchronize(s));

@@ -57,7 +57,7 @@ template <class T> struct DevBuf {
 // FFT tables of one size on one device
 struct FftPlan {
     StftConfig cfg;
-    DevBuf<float2> tw, split;
+    DevBuf<float2> tw, split, twr;
 };
 
 // everything that depends on (sr, win, n_fft, n_mel): the `windows` / `mel_fbs` caches, lib.rs:76-77

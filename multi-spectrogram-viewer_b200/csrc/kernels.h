@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "device_common.cuh"
@@ -43,6 +44,8 @@ int stft_warp2_warps();                                    // warps per CTA (8 u
 
 // FFT twiddle tables for one size (host vectors -> caller uploads).
 void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);
+// twiddles of the Stockham passes, per pass and r-major (what the block kernel of this size loads)
+std::vector<float2> make_fft_pass_tables(int h, int pts);
 
 // K2: global dB range (lib.rs:193-209)
 cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s);

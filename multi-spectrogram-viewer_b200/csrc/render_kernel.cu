@@ -313,45 +313,41 @@ __host__ __device__ constexpr size_t fp_smem(int tv, int th)
 // b = stop i+1:  round(ratio*b + (1-ratio)*a) = floor(a + 0.5 + ratio*(b - a)), one FMA and one
 // conversion per channel.  The single rounding of the FMA can differ from the reference's three only when
 // the exact value lies within ~3e-5 of a rounding boundary (about 1 byte in 10^4, by 1 LSB).
-// A segment is ONE 16-byte shared load: its six numbers are stored as fp16 pairs -- stops are integers
-// <= 255 and a + 0.5 has 9 significant bits, so fp16 holds them exactly.  (The render kernels are bound
-// by the shared-memory / L1 data pipe; two 128-bit loads per pixel were a third of their wavefronts.)
-__device__ __forceinline__ unsigned grey_to_rgba_fast(float x, const uint4 *cmab)
+// The table lives in constant memory, as floats: {r.a, r.d, g.a, g.d} {b.a, b.d, -, -} per segment.  An indexed constant
+// load replays once per DISTINCT index in the warp (neighbouring pixels of a row mostly share one or two segments) and
+// does not touch the shared-memory / L1 data pipe that bounds the render kernels (C5 K3 3.92 -> 3.69 ms against a
+// 16-byte shared-memory entry per pixel, which was a sixth of the kernel's wavefronts).
+struct CmSeg { float4 rg, b; };
+__constant__ CmSeg kCmConst[9] = {
+#define SGX_SEG(r0, g0, b0, r1, g1, b1) {{r0 + 0.5f, (float)(r1 - r0), g0 + 0.5f, (float)(g1 - g0)}, {b0 + 0.5f, (float)(b1 - b0), 0.0f, 0.0f}}
+    SGX_SEG(0, 0, 4, 27, 12, 65), SGX_SEG(27, 12, 65, 74, 12, 107), SGX_SEG(74, 12, 107, 120, 28, 109),
+    SGX_SEG(120, 28, 109, 165, 44, 96), SGX_SEG(165, 44, 96, 207, 68, 70), SGX_SEG(207, 68, 70, 237, 105, 37),
+    SGX_SEG(237, 105, 37, 251, 155, 6), SGX_SEG(251, 155, 6, 247, 209, 61), SGX_SEG(247, 209, 61, 252, 255, 164)
+#undef SGX_SEG
+};
+__device__ __forceinline__ unsigned grey_to_rgba_const(float x)
 {
     const float position = __fmul_rn(10.0f, x);
     const float fl = floorf(position);
     const int idx = min(__float2int_rz(fl), 8);
     const float ratio = __fsub_rn(position, fl);
-    const uint4 q = cmab[idx];
-    const float2 r = __half22float2(*reinterpret_cast<const __half2 *>(&q.x));
-    const float2 g = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&q.z));
-    const unsigned cr = __float2uint_rd(fmaf(ratio, r.y, r.x));
-    const unsigned cg = __float2uint_rd(fmaf(ratio, g.y, g.x));
+    const float4 rg = kCmConst[idx].rg;
+    const float4 b = kCmConst[idx].b;
+    const unsigned cr = __float2uint_rd(fmaf(ratio, rg.y, rg.x));
+    const unsigned cg = __float2uint_rd(fmaf(ratio, rg.w, rg.z));
     const unsigned cb = __float2uint_rd(fmaf(ratio, b.y, b.x));
     const unsigned px = cr | (cg << 8) | (cb << 16) | 0xff000000u;
     return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
 }
-// segment i of the colour map: per channel half2(stop i + 0.5, stop i+1 - stop i)
-__device__ __forceinline__ void fill_colour_table(uint4 *cmab, int tid)
-{
-    if (tid < 9) {
-        unsigned w[3];
-        for (int c = 0; c < 3; ++c) {
-            const __half2 h = __floats2half2_rn((float)kColormap[tid][c] + 0.5f, (float)kColormap[tid + 1][c] - (float)kColormap[tid][c]);
-            w[c] = *reinterpret_cast<const unsigned *>(&h);
-        }
-        cmab[tid] = make_uint4(w[0], w[1], w[2], 0u);
-    }
-}
 
+// (packed FP32 pairs -- FFMA2 -- in the two tap loops were measured and change nothing, 3.905 vs 3.923 ms: the kernel is
+// bound by the shared-memory / L1 data pipe, not by issue slots)
 template <int TV, int TH, bool FROM_DB, int CH>
 __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas : 1) render_fast_kernel(const RenderLaunch L)
 {
     constexpr int RCAP = fp_cap(TV), FCAP = fp_cap(TH), GP = FCAP; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
-    __shared__ uint4 cmab[9];
-    float *G = rsm;
+     float *G = rsm;
     float *Tm = rsm + RCAP * GP;         // [frame][out row]
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
     const int nwidth = tr->nwidth, nheight = tr->nheight;
@@ -361,7 +357,6 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
     if (ox0 >= ox_end || oy0 >= nheight) return;
     const int pxc = min(kFpTile, ox_end - ox0), pyc = min(kFpTile, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    fill_colour_table(cmab, tid);
 
     const int *__restrict__ h_left = tr->h_left;
     const int *__restrict__ v_left = tr->v_left;
@@ -479,7 +474,7 @@ __global__ void __launch_bounds__(kRenderThreads, (TV <= 8 && TH <= 8) ? kFpCtas
 #pragma unroll
                 for (int j = 0; j < 4; ++j, pix += opitch) {
                     if (rq * 4 + j < pyc) {
-                        const unsigned c = grey_to_rgba_fast(clamp_fin(t[j]), cmab);
+                        const unsigned c = grey_to_rgba_const(clamp_fin(t[j]));
                         if (CH == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
                         else { outp[pix * 3] = (unsigned char)c; outp[pix * 3 + 1] = (unsigned char)(c >> 8); outp[pix * 3 + 2] = (unsigned char)(c >> 16); }
                     }
@@ -514,8 +509,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const Re
 {
     const int RCAP = L.rv_max, GP = L.fc; // G [row][frame], pitch = frame capacity
     extern __shared__ __align__(16) float rsm[];
-    __shared__ uint4 cmab[9];
-    float *G = rsm;
+     float *G = rsm;
     float *Tm = rsm + (size_t)RCAP * GP;  // [frame][out row], pitch TP
     const int TP = L.py + 4;              // 68 / 36 / 20: multiples of 4 with an odd quarter
     const RenderTrack *__restrict__ tr = L.tracks + blockIdx.z;
@@ -526,7 +520,6 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const Re
     if (ox0 >= ox_end || oy0 >= nheight) return;
     const int pxc = min(L.px, ox_end - ox0), pyc = min(L.py, nheight - oy0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    fill_colour_table(cmab, tid);
 
     const int *__restrict__ h_left = tr->h_left;
     const int *__restrict__ v_left = tr->v_left;
@@ -689,7 +682,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) render_wide_kernel(const Re
 #pragma unroll
                 for (int j = 0; j < 4; ++j, pix += opitch) {
                     if (rq * 4 + j < pyc) {
-                        const unsigned c = grey_to_rgba_fast(clamp_fin(t[k][j] * rhs), cmab);
+                        const unsigned c = grey_to_rgba_const(clamp_fin(t[k][j] * rhs));
                         if (CH == 4) reinterpret_cast<unsigned *>(outp)[pix] = c;
                         else { outp[pix * 3] = (unsigned char)c; outp[pix * 3 + 1] = (unsigned char)(c >> 8); outp[pix * 3 + 2] = (unsigned char)(c >> 16); }
                     }

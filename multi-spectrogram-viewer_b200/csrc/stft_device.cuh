@@ -184,6 +184,7 @@ struct TileLoc {
     long long S0, A0;
     bool tma;
     bool raw2; // the tile holds raw interleaved stereo f32 (2 floats per sample), summed when the first pass loads it
+    bool i16;  // the tile holds raw mono int16 samples (audio.rs:16-19 scale applied when the first pass loads it)
 };
 // `lo` is a lower bound of the track index (a CTA visits tiles, hence tracks, in rising order)
 __device__ __forceinline__ int find_track(const StftLaunch &L, int tile_id, int lo)
@@ -197,30 +198,36 @@ __device__ __forceinline__ int find_track(const StftLaunch &L, int tile_id, int 
 }
 // `td` may be the descriptor in global memory or the CTA's shared-memory copy of it
 __device__ __forceinline__ void locate_tile(const StftLaunch &L, int F, int tile_id, int trk, const StftTrack *td, TileLoc &o,
-                                            bool allow_raw2)
+                                            bool allow_raw2, bool allow_i16 = false)
 {
     o.trk = trk;
     o.t0 = (tile_id - td->tile_begin) * L.frames_per_tile;
     o.nfr = min(L.frames_per_tile, td->n_frames - o.t0);
     const long long origin = td->origin;
     o.S0 = (long long)(td->frame0 + o.t0) * td->hop - td->win / 2 - td->pad_l; // first (global) sample of the tile's first FFT frame
-    o.off0 = (int)((o.S0 - origin) & 3);
+    // 16-byte granules of the bulk copy: 4 f32 samples, 8 int16 samples
+    const bool want16 = allow_i16 && td->fmt == PCM_I16 && td->ch == 1;
+    const int gran = want16 ? 8 : 4;
+    o.off0 = (int)((o.S0 - origin) & (gran - 1));
     o.A0 = o.S0 - o.off0; // global index whose LOCAL position is 16-byte aligned: start of the staged tile
     o.len = o.off0 + (o.nfr - 1) * td->hop + F;
-    o.len4 = (o.len + 3) & ~3;
-    // a tile that lies inside the track (no reflection), f32, 16-byte aligned: one TMA bulk copy -- of the samples
-    // (mono) or of the raw interleaved pairs (stereo; the channels are summed when the first pass loads them, which
-    // needs every frame of the tile to start on an even sample and twice the room)
-    const bool plain = L.staged && td->fmt == PCM_F32 && ((reinterpret_cast<uintptr_t>(td->pcm) & 15) == 0) &&
-                       o.A0 >= 0 && o.A0 + o.len4 <= td->n && o.A0 - origin >= 0 && o.A0 - origin + o.len4 <= td->avail;
+    o.len4 = (o.len + gran - 1) & ~(gran - 1);
+    // a tile that lies inside the track (no reflection), 16-byte aligned: one TMA bulk copy -- of the f32 samples (mono),
+    // of the raw interleaved f32 pairs (stereo; the channels are summed when the first pass loads them, which needs every
+    // frame of the tile to start on an even sample and twice the room), or of the raw int16 samples (mono; converted
+    // and scaled when the first pass loads them)
+    const bool inside = L.staged && ((reinterpret_cast<uintptr_t>(td->pcm) & 15) == 0) &&
+                        o.A0 >= 0 && o.A0 + o.len4 <= td->n && o.A0 - origin >= 0 && o.A0 - origin + o.len4 <= td->avail;
+    const bool plain = inside && td->fmt == PCM_F32;
     o.raw2 = allow_raw2 && plain && td->ch == 2 && ((td->hop | o.off0) & 1) == 0 && 2 * o.len4 <= L.tile_floats;
-    o.tma = (plain && td->ch == 1) || o.raw2;
+    o.i16 = want16 && inside;
+    o.tma = (plain && td->ch == 1) || o.raw2 || o.i16;
 }
 __device__ __forceinline__ void issue_tile_copy(const StftTrack *td, const TileLoc &o, float *tile, unsigned long long *mbar)
 {
-    const unsigned spf = o.raw2 ? 2u : 1u; // floats per sample in the staged tile
-    mbar_expect_tx(mbar, (unsigned)o.len4 * 4u * spf);
-    bulk_copy_g2s(tile, reinterpret_cast<const float *>(td->pcm) + (o.A0 - td->origin) * spf, (unsigned)o.len4 * 4u * spf, mbar);
+    const unsigned bps = o.i16 ? 2u : (o.raw2 ? 8u : 4u); // bytes per sample in the staged tile
+    mbar_expect_tx(mbar, (unsigned)o.len4 * bps);
+    bulk_copy_g2s(tile, reinterpret_cast<const char *>(td->pcm) + (o.A0 - td->origin) * (long long)bps, (unsigned)o.len4 * bps, mbar);
 }
 
 } // namespace

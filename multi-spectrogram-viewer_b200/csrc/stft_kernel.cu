@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -51,17 +52,41 @@ template <int G, int NT> __device__ __forceinline__ void group_sync(int grp)
     else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NT) : "memory");
 }
 
+// where the twiddles of the pass with input stride product NS start in the per-pass table (make_fft_pass_tables)
+__host__ __device__ constexpr int pass_table_offset(int h, int pts, int ns_of_pass)
+{
+    int off = 0;
+    for (int ns = 1; ns < ns_of_pass;) {
+        const int r = (h / ns >= pts) ? pts : h / ns;
+        if (ns > 1) off += (r - 1) * ns;
+        ns *= r;
+    }
+    return off;
+}
+
 template <int H, int PTS, int V, int G, int R, int NS>
 __device__ __forceinline__ void fft_pass(pk (&re)[PTS][V / 2], pk (&im)[PTS][V / 2], float *sre,
-                                         float *sim, int gt, int grp, const float2 *__restrict__ tw)
+                                         float *sim, int gt, int grp, const float2 *__restrict__ twr)
 {
     constexpr int VP = V / 2;
     constexpr int NT = H / PTS, NB = PTS / R;
     if constexpr (NS > 1) {
-        // twiddle bases first: the table loads fly while the shared loads and the barrier complete
-        float2 w1[NB];
+        // Twiddles first: the table loads fly while the shared loads and the barrier complete.  Every w[r] =
+        // exp(-2 pi i r k / (NS R)) comes from a table, correctly rounded from f64 -- like the precomputed twiddles of
+        // rustfft's Radix4 (realfft.rs:94).  Forming the powers by complex products from one table entry left the
+        // twiddles 3-5 ulp off, which put the noise floor of the spectrum (the bins 60+ dB below a frame's peak) 5-6x
+        // above the reference's: see tests/parity.py, the f64-truth gate.  The table of a pass is r-major,
+        // twr[(r - 1) NS + k], so that the lanes of a warp (consecutive k) read consecutive entries: one or two
+        // 128-byte lines per load (the natural table tw[r k H / (NS R)] is strided: 8 to 28 lines per load, and cost
+        // 11 % of the kernel).
+        constexpr int OFF = pass_table_offset(H, PTS, NS);
+        float2 wt[NB][R];
 #pragma unroll
-        for (int q = 0; q < NB; ++q) w1[q] = __ldg(tw + ((gt + q * NT) & (NS - 1)) * (H / (NS * R)));
+        for (int q = 0; q < NB; ++q) {
+            const int k = (gt + q * NT) & (NS - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) wt[q][r] = __ldg(twr + OFF + (r - 1) * NS + k);
+        }
         // element gt + q*NT + r*H/R: the offsets are multiples of 8, so pad() is linear in them
         static_assert(NT % 8 == 0 && (H / R) % 8 == 0, "padded addressing assumes multiples of 8");
         const int sbase = padi(gt) * V;
@@ -76,27 +101,7 @@ __device__ __forceinline__ void fft_pass(pk (&re)[PTS][V / 2], pk (&im)[PTS][V /
         group_sync<G, NT>(grp); // every thread has its inputs: the buffer may be overwritten
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
-            // w[r] = exp(-2 pi i r k / (NS R)): one table load, the powers by complex products
-            // (at most 3 products deep: error a few ulp, far inside the 1e-4 magnitude tolerance)
-            float2 w[R];
-            w[1] = w1[q];
-            if constexpr (R >= 4) {
-                w[2] = make_float2(w[1].x * w[1].x - w[1].y * w[1].y, 2.0f * w[1].x * w[1].y);
-                w[3] = make_float2(w[2].x * w[1].x - w[2].y * w[1].y, w[2].x * w[1].y + w[2].y * w[1].x);
-            }
-            if constexpr (R >= 8) {
-                w[4] = make_float2(w[2].x * w[2].x - w[2].y * w[2].y, 2.0f * w[2].x * w[2].y);
-                w[5] = make_float2(w[4].x * w[1].x - w[4].y * w[1].y, w[4].x * w[1].y + w[4].y * w[1].x);
-                w[6] = make_float2(w[3].x * w[3].x - w[3].y * w[3].y, 2.0f * w[3].x * w[3].y);
-                w[7] = make_float2(w[4].x * w[3].x - w[4].y * w[3].y, w[4].x * w[3].y + w[4].y * w[3].x);
-            }
-            if constexpr (R >= 16) {
-                auto cm = [](float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); };
-                w[8] = make_float2(w[4].x * w[4].x - w[4].y * w[4].y, 2.0f * w[4].x * w[4].y);
-                w[9] = cm(w[8], w[1]); w[10] = cm(w[8], w[2]); w[11] = cm(w[8], w[3]); w[12] = cm(w[8], w[4]);
-                w[13] = cm(w[8], w[5]); w[14] = cm(w[8], w[6]); w[15] = cm(w[8], w[7]);
-            }
-            static_assert(R <= 16, "twiddle powers are written out for radix <= 16");
+            const float2 (&w)[R] = wt[q];
 #pragma unroll
             for (int r = 1; r < R; ++r) {
 #pragma unroll
@@ -164,12 +169,12 @@ __device__ __forceinline__ void fft_pass(pk (&re)[PTS][V / 2], pk (&im)[PTS][V /
 // Runs the passes whose input stride product NS is below NS_END (H: all passes).
 template <int H, int PTS, int V, int G, int NS, int NS_END>
 __device__ __forceinline__ void run_passes(pk (&re)[PTS][V / 2], pk (&im)[PTS][V / 2], float *sre,
-                                           float *sim, int gt, int grp, const float2 *__restrict__ tw)
+                                           float *sim, int gt, int grp, const float2 *__restrict__ twr)
 {
     if constexpr (NS < NS_END) {
         constexpr int R = (H / NS >= PTS) ? PTS : (H / NS);
-        fft_pass<H, PTS, V, G, R, NS>(re, im, sre, sim, gt, grp, tw);
-        run_passes<H, PTS, V, G, NS * R, NS_END>(re, im, sre, sim, gt, grp, tw);
+        fft_pass<H, PTS, V, G, R, NS>(re, im, sre, sim, gt, grp, twr);
+        run_passes<H, PTS, V, G, NS * R, NS_END>(re, im, sre, sim, gt, grp, twr);
     }
 }
 
@@ -193,14 +198,16 @@ template <int LOG2H, int PTS, int V, int G, int MC> struct K1Traits {
 // MEL: the launch projects onto a mel filterbank (MODE_MEL_DB).  A compile-time flag rather than a test of
 // L.mode: the code of the other output modes (and their branch targets) is then absent from the mel kernel's
 // instruction stream, which is long enough for instruction fetch to show up in the stall profile.
-// RAW2: f32 stereo tiles are staged as raw interleaved pairs by TMA and summed by the first pass (its own
-// instantiation: the extra first-pass variant costs the mono kernels 2 % when it merely sits in their code).
-template <int LOG2H, int PTS, int V, int G, int MC, bool MEL, bool RAW2>
+// LOADER: which raw tiles the first pass can read besides mono f32 -- 1: f32 stereo tiles, staged as raw interleaved
+// pairs by TMA and summed by the first pass; 2: int16 mono tiles, staged as 16-bit samples and converted by it.
+// Instantiations of their own: an extra first-pass variant costs 2-8 % when it merely sits in a kernel's code.
+template <int LOG2H, int PTS, int V, int G, int MC, bool MEL, int LOADER>
 __global__ void __launch_bounds__(K1Traits<LOG2H, PTS, V, G, MC>::THREADS, MC)
 stft_db_kernel(const StftLaunch L)
 {
     using TR = K1Traits<LOG2H, PTS, V, G, MC>;
     constexpr int H = TR::H, NT = TR::NT, THREADS = TR::THREADS, PADH = TR::PADH, F = 2 * H;
+    constexpr bool RAW2 = LOADER == 1, RAW16 = LOADER == 2; // which raw tiles the first pass of this instantiation reads
     static_assert(NT >= 32 && (NT % 32) == 0, "a group must be whole warps");
     static_assert(G <= 15, "one named barrier (1..15) per group");
 
@@ -249,7 +256,7 @@ stft_db_kernel(const StftLaunch L)
     int trk_end = s_trk_end;
     const StftTrack *td = &s_td;
     TileLoc cur;
-    locate_tile(L, F, blockIdx.x, s_trk, td, cur, RAW2);
+    locate_tile(L, F, blockIdx.x, s_trk, td, cur, RAW2, RAW16);
     if (cur.tma && tid == 0) issue_tile_copy(td, cur, tile, mbar);
 
     float vmax = -INFINITY, vmin = INFINITY;
@@ -277,7 +284,7 @@ stft_db_kernel(const StftLaunch L)
             enter_track(tile_id, cur.trk);
             trk_end = s_trk_end;
         }
-        locate_tile(L, F, tile_id, s_trk, td, cur, RAW2);
+        locate_tile(L, F, tile_id, s_trk, td, cur, RAW2, RAW16);
     }
     if (cur.trk != range_trk) { range_trk = cur.trk; vmax = -INFINITY; vmin = INFINITY; }
     const PcmView pv{td->pcm, td->n, td->ch, td->fmt, td->origin, td->avail};
@@ -365,7 +372,7 @@ stft_db_kernel(const StftLaunch L)
         pk re[PTS][VP], im[PTS][VP]; // pair i = frames 2i, 2i+1 of the group
 
         // ---- first-pass inputs: z[m] = g[2m] + i g[2m+1], g = sample * window ---------------------
-        if (L.staged && vec_ok && !(RAW2 && cur.raw2)) {
+        if (L.staged && vec_ok && !(RAW2 && cur.raw2) && !(RAW16 && cur.i16)) {
             // every frame of the tile starts on an even float: one 64-bit shared load per point
             const float *fb[V];
 #pragma unroll
@@ -378,6 +385,23 @@ stft_db_kernel(const StftLaunch L)
                 for (int v = 0; v < V; ++v) {
                     const float2 x = *reinterpret_cast<const float2 *>(fb[v] + 2 * p * NT);
                     pk_set<VP>(re[p], v, x.x * w.x); pk_set<VP>(im[p], v, x.y * w.y);
+                }
+            }
+        } else if (RAW16 && L.staged && vec_ok && cur.i16) {
+            // raw int16 tile: one 32-bit shared load brings the two samples of a point; audio.rs:16-19 scales them
+            const short *tb = reinterpret_cast<const short *>(tile);
+            const short *fb[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) fb[v] = tb + off0 + min(fl0 + v, nfr - 1) * hop + 2 * gt;
+#pragma unroll
+            for (int p = 0; p < PTS; ++p) {
+                const int n = 2 * (gt + p * NT);
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(win_f + n));
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const unsigned u = *reinterpret_cast<const unsigned *>(fb[v] + 2 * p * NT);
+                    const float x0 = (float)(short)(u & 0xffffu) * (1.0f / 32768.0f), x1 = (float)(short)(u >> 16) * (1.0f / 32768.0f);
+                    pk_set<VP>(re[p], v, x0 * w.x); pk_set<VP>(im[p], v, x1 * w.y);
                 }
             }
         } else if (RAW2 && L.staged && vec_ok) {
@@ -404,7 +428,11 @@ stft_db_kernel(const StftLaunch L)
                 for (int v = 0; v < V; ++v) {
                     const int fl = min(fl0 + v, nfr - 1);
                     float x0, x1;
-                    if (L.staged) {
+                    if (RAW16 && L.staged && cur.i16) { // odd hop: frames of an int16 tile that start on an odd sample
+                        const short *tb = reinterpret_cast<const short *>(tile);
+                        const int b = off0 + fl * hop + n;
+                        x0 = (float)tb[b] * (1.0f / 32768.0f); x1 = (float)tb[b + 1] * (1.0f / 32768.0f);
+                    } else if (L.staged) {
                         const int b = off0 + fl * hop + n;
                         x0 = tile[b]; x1 = tile[b + 1];
                     } else {
@@ -431,7 +459,7 @@ stft_db_kernel(const StftLaunch L)
                         const StftTrack *ntd = td;
                         int ntrk = cur.trk;
                         if (nt >= trk_end) { ntrk = find_track(L, nt, cur.trk); ntd = L.tracks + ntrk; }
-                        locate_tile(L, F, nt, ntrk, ntd, nx, RAW2);
+                        locate_tile(L, F, nt, ntrk, ntd, nx, RAW2, RAW16);
                         if (nx.tma) issue_tile_copy(ntd, nx, tile, mbar);
                     }
                 }
@@ -496,7 +524,7 @@ stft_db_kernel(const StftLaunch L)
             // Butterfly j of the last pass (radix RL, NSL = H/RL) produces Z[j + r NSL]; the conjugate
             // partner of that bin comes out of butterfly NSL - j.  Each thread therefore runs butterfly
             // PAIRS (j, NSL - j): the spectrum never returns to shared memory and the split costs no loads.
-            run_passes<H, PTS, V, G, 1, H / RL>(re, im, sre, sim, gt, grp, L.tw);
+            run_passes<H, PTS, V, G, 1, H / RL>(re, im, sre, sim, gt, grp, L.twr);
             constexpr int NSL = H / RL, NPR = (PTS / RL) / 2;
             static_assert(NSL % 8 == 0, "padded addressing assumes multiples of 8");
             int bA[NPR], bB[NPR];
@@ -532,9 +560,9 @@ stft_db_kernel(const StftLaunch L)
             for (int b = 0; b < 2 * NPR; ++b) {
                 float2 w[RL];
                 w[1] = (b & 1) ? wB[b >> 1] : wA[b >> 1];
-                if constexpr (RL >= 4) {
-                    w[2] = make_float2(w[1].x * w[1].x - w[1].y * w[1].y, 2.0f * w[1].x * w[1].y);
-                    w[3] = make_float2(w[2].x * w[1].x - w[2].y * w[1].y, w[2].x * w[1].y + w[2].y * w[1].x);
+                if constexpr (RL >= 4) { // table twiddles here too (j < H / RL, so r j < H)
+                    const int jb = (b & 1) ? bB[b >> 1] : bA[b >> 1];
+                    w[2] = __ldg(L.tw + 2 * jb); w[3] = __ldg(L.tw + 3 * jb);
                 }
                 static_assert(RL <= 4, "fused last pass is written for radix 2 and 4");
 #pragma unroll
@@ -584,7 +612,7 @@ stft_db_kernel(const StftLaunch L)
                 }
             }
         } else {
-        run_passes<H, PTS, V, G, 1, H>(re, im, sre, sim, gt, grp, L.tw);
+        run_passes<H, PTS, V, G, 1, H>(re, im, sre, sim, gt, grp, L.twr);
         constexpr int NP = PTS / 2;
         const int pa0 = padi(gt) * V;      // element k = gt + q NT      -> pa0 + 9 q NT / 8
         const int pb0 = padi(H - gt) * V;  // element H - k (k > 0)      -> pb0 - 9 q NT / 8
@@ -864,11 +892,11 @@ int resident_sms()
     return sms > 0 ? sms : 148;
 }
 
-template <int LOG2H, int PTS, int V, int G, int MC, bool MEL, bool RAW2>
+template <int LOG2H, int PTS, int V, int G, int MC, bool MEL, int LOADER>
 cudaError_t launch_one_mode(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
     using TR = K1Traits<LOG2H, PTS, V, G, MC>;
-    auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC, MEL, RAW2>;
+    auto kern = stft_db_kernel<LOG2H, PTS, V, G, MC, MEL, LOADER>;
     cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     if (e != cudaSuccess) return e;
     // persistent CTAs: as many as are resident at once, each walking tiles blockIdx.x + k gridDim.x
@@ -880,11 +908,16 @@ cudaError_t launch_one_mode(const StftLaunch &L, size_t smem, cudaStream_t strea
 template <int LOG2H, int PTS, int V, int G, int MC>
 cudaError_t launch_one(const StftLaunch &L, size_t smem, cudaStream_t stream)
 {
-    // raw stereo staging exists for the mel kernels (the viewer's default scale); linear launches gather stereo tiles
+    // launches that hold f32 stereo (1) or int16 mono (2) tracks use an instantiation whose first pass also reads
+    // that kind of raw staged tile; mono f32 launches keep the lean one (0)
+    const int ld = L.stereo_raw;
     if (L.mode == MODE_MEL_DB)
-        return L.stereo_raw ? launch_one_mode<LOG2H, PTS, V, G, MC, true, true>(L, smem, stream)
-                            : launch_one_mode<LOG2H, PTS, V, G, MC, true, false>(L, smem, stream);
-    return launch_one_mode<LOG2H, PTS, V, G, MC, false, false>(L, smem, stream);
+        return ld == 1 ? launch_one_mode<LOG2H, PTS, V, G, MC, true, 1>(L, smem, stream)
+             : ld == 2 ? launch_one_mode<LOG2H, PTS, V, G, MC, true, 2>(L, smem, stream)
+                       : launch_one_mode<LOG2H, PTS, V, G, MC, true, 0>(L, smem, stream);
+    return ld == 1 ? launch_one_mode<LOG2H, PTS, V, G, MC, false, 1>(L, smem, stream)
+         : ld == 2 ? launch_one_mode<LOG2H, PTS, V, G, MC, false, 2>(L, smem, stream)
+                   : launch_one_mode<LOG2H, PTS, V, G, MC, false, 0>(L, smem, stream);
 }
 
 } // namespace
@@ -1048,6 +1081,26 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, 
     }
     t.sample_floats = sample_floats;
     t.smem_bytes = 16 + (size_t)(t.tile_floats + t.bank_floats) * sizeof(float) + cfg.fft_smem;
+    return t;
+}
+
+// Twiddles of the Stockham passes of stft_db_kernel<.., PTS, ..>, pass after pass, r-major inside a pass:
+// exp(-2 pi i r k / (NS R)) at pass_table_offset(h, pts, NS) + (r - 1) NS + k  (see fft_pass)
+std::vector<float2> make_fft_pass_tables(int h, int pts)
+{
+    const double pi = 3.14159265358979323846264338327950288;
+    std::vector<float2> t;
+    for (int ns = 1; ns < h;) {
+        const int r = (h / ns >= pts) ? pts : h / ns;
+        if (ns > 1)
+            for (int rr = 1; rr < r; ++rr)
+                for (int k = 0; k < ns; ++k) {
+                    const double a = -2.0 * pi * (double)rr * (double)k / ((double)ns * (double)r);
+                    t.push_back(make_float2((float)cos(a), (float)sin(a)));
+                }
+        ns *= r;
+    }
+    if (t.empty()) t.push_back(make_float2(1.0f, 0.0f));
     return t;
 }
 

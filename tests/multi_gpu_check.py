@@ -87,7 +87,26 @@ def main():
     print(f"rank {rank}: time-sharded strip [{ob}, {ob + oc}) identical to the single-GPU image: {same}", flush=True)
     ok = ok and same
     st2.close(); one.close()
-    flag = torch.tensor([1 if ok else 0], device="cuda")
+    # ---- ONE process, several GPUs: a single handle over all devices (sgx_mt_new_sharded) -- rank 0 only ------------
+    dist.barrier()
+    if rank == 0 and world > 1:
+        allg = msv.MultiTrack(devices=list(range(world)))
+        assert allg.device_count()[0] == world
+        changed = allg.add_tracks_pcm(list(range(n_tracks)), tracks, srs)
+        same = changed and (allg.get_max_db(), allg.get_min_db()) == want_range and abs(allg.get_max_sec() - ref.get_max_sec()) < 1e-6
+        imgs = allg.get_spec_images(list(range(n_tracks)), 100.0, 300, 4)
+        for t, im in enumerate(imgs):
+            same = same and np.array_equal(im, ref.get_spec_image_rgba(t, 100.0, 300)) and allg.get_sr(t) == srs[t]
+        allg.remove_track(3)
+        ref.remove_track(3)
+        same = same and (allg.get_max_db(), allg.get_min_db()) == (ref.get_max_db(), ref.get_min_db())
+        same = same and np.array_equal(allg.get_spec_image(5, 100.0, 300), ref.get_spec_image(5, 100.0, 300))
+        print(f"rank 0: one handle over {world} GPUs identical to the single-GPU handle: {same}", flush=True)
+        ok = ok and same
+        allg.close()
+        assert torch.cuda.current_device() == local, "a call into libsgx.so left another device current"
+    dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     sm.close(); ref.close()
     dist.barrier()

@@ -103,6 +103,47 @@ def test_wav_reader_and_errors(msv, tmp_path):
     assert e.value.code == msv.SGX_ERR_IO
 
 
+def test_wav_reader_survives_hostile_headers(msv, tmp_path):
+    """Chunk sizes come from the file: a data / fmt / unknown chunk that announces 4 GiB must neither allocate that
+    much nor loop; a truncated data chunk yields the samples that are there (round-1 advisor finding)."""
+    import struct
+
+    import numpy as np
+
+    fmt = struct.pack("<HHIIHH", 1, 1, 8000, 16000, 2, 16)
+    body = np.arange(100, dtype=np.int16).tobytes()
+
+    def wav(chunks):
+        payload = b"WAVE" + b"".join(tag + struct.pack("<I", size) + data for tag, size, data in chunks)
+        return b"RIFF" + struct.pack("<I", len(payload)) + payload
+
+    p = tmp_path / "huge_data.wav"     # data chunk claims 0xFFFFFFFF bytes, holds 200
+    p.write_bytes(wav([(b"fmt ", 16, fmt), (b"data", 0xFFFFFFFF, body)]))
+    x, sr = msv.open_audio_file(str(p))
+    assert sr == 8000 and x.shape == (1, 100) and np.array_equal(x[0], np.arange(100, dtype=np.float32) / 32768)
+    for name, chunks in (("huge_fmt.wav", [(b"fmt ", 0xFFFFFFF0, fmt), (b"data", 200, body)]),
+                         ("huge_junk.wav", [(b"JUNK", 0xFFFFFFFF, b"xx"), (b"fmt ", 16, fmt), (b"data", 200, body)])):
+        q = tmp_path / name
+        q.write_bytes(wav(chunks))
+        with pytest.raises(msv.SgxError) as e:
+            msv.open_audio_file(str(q))
+        assert e.value.code == msv.SGX_ERR_IO
+
+
+def test_reference_arm_does_not_import_the_gpu_package():
+    """bench.py --impl reference times the CPU restatement only: neither msv_b200 nor libsgx.so may be loaded by it
+    (round-1 review: the arm imported the package for three integers)."""
+    import subprocess
+    import sys
+    code = ("import runpy, sys; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'c1', '--steps', '1', '--warmup', '0'];\n"
+            "try:\n    runpy.run_path('bench.py', run_name='__main__')\nexcept SystemExit as e:\n    assert not e.code, e.code\n"
+            "bad = [m for m in sys.modules if 'msv_b200' in m or 'multi-spectrogram-viewer_b200' in m]\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert not bad and 'libsgx' not in maps, (bad, 'libsgx' in maps)\nprint('REFERENCE ARM CLEAN')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "REFERENCE ARM CLEAN" in r.stdout and '"impl": "reference"' in r.stdout, r.stdout[-800:] + r.stderr[-800:]
+
+
 def test_rust_sys_crate_is_in_step_with_the_header():
     """bindings/rust/sgx-sys/src/lib.rs (uncompiled: no Rust toolchain here) is generated from include/sgx.h and
     declares every entry point the header does."""

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 import synth
-from parity import DB_ATOL, MAG_RTOL, PX_LSB, assert_db_close, assert_pixels_close, assert_range_close, db_report
+from parity import (DB_ATOL, MAG_RTOL, PX_LSB, assert_db_close, assert_db_vs_truth, assert_min_db_vs_truth, assert_pixels_close,
+                    assert_range_close, db_report)
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -109,6 +110,7 @@ def test_default_mel_db_parity(msv, orc, sr):
     got = msv.melspectrogram_db(x, win, hop, n_fft, None, fb)
     truth = orc.calc_spec_f64(x, win, hop, n_fft, None, fb)
     e, m = assert_db_close(got, ref, f"mel sr={sr}")
+    assert_db_vs_truth(got, ref, truth, f"mel sr={sr}")
     print(f"mel dB sr={sr} M={fb.shape[1]}: gpu-vs-oracle {e:.2e} dB / {m:.2e} mag; vs truth gpu {db_err(got, truth):.2e} oracle {db_err(ref, truth):.2e}")
 
 
@@ -120,6 +122,8 @@ def test_fixed_mel_db_parity(msv, orc, n_fft, hop, n_mel, sr):
     ref = orc.calc_spec(x, n_fft, hop, n_fft, None, fb)
     got = msv.melspectrogram_db(x, n_fft, hop, n_fft, None, fb)
     e, m = assert_db_close(got, ref, f"mel-{n_mel} n_fft={n_fft}")
+    if not (ref <= -359.0).any():   # C3 shape and friends: anchored on the f64 truth over the whole display range
+        assert_db_vs_truth(got, ref, orc.calc_spec_f64(x, n_fft, hop, n_fft, None, fb), f"mel-{n_mel} n_fft={n_fft}")
     print(f"mel-{n_mel} n_fft={n_fft}: {e:.2e} dB / {m:.2e} mag")
     # empty filters (no bin inside) sit on the -360 dB floor in both
     assert np.array_equal(got <= -359.0, ref <= -359.0)
@@ -133,6 +137,7 @@ def test_linear_db_parity(msv, orc, n_fft):
     got = msv.melspectrogram_db(x, n_fft, n_fft // 4, n_fft, None, None)
     e, m = assert_db_close(got, ref, f"linear n_fft={n_fft}")
     truth = orc.calc_spec_f64(x, n_fft, n_fft // 4, n_fft, None, None)
+    assert_db_vs_truth(got, ref, truth, f"linear n_fft={n_fft}")
     print(f"linear dB n_fft={n_fft}: {e:.2e} dB / {m:.2e} mag; vs truth gpu {db_err(got, truth):.2e} oracle {db_err(ref, truth):.2e}")
 
 
@@ -236,6 +241,18 @@ def test_multitrack_six_rates_end_to_end(msv, orc):
     mt = msv.MultiTrack()
     assert mt.add_tracks_pcm(list(range(6)), wavs, srs)
     assert_range_close((mt.get_max_db(), mt.get_min_db()), (mx, mn), what="six rates")
+    # the committed range against the f64 truth: the engine's min_db may not be further off than the f32 reference's
+    truths = []
+    for w, sr in zip(wavs, srs):
+        win, hop, n_fft = msv.track_params(sr)
+        truths.append(orc.calc_spec_f64(w, win, hop, n_fft, None, msv.calc_mel_fb_default(sr, n_fft)))
+    tmx = min(max(float(t.max()) for t in truths), 0.0)
+    tmn = max(min(float(t.min()) for t in truths), tmx - 120.0)   # lib.rs:208-209 in f64
+    assert_min_db_vs_truth(mt.get_min_db(), mn, tmn, "six rates")
+    for i, t in enumerate(truths):
+        win, hop, n_fft = msv.track_params(srs[i])
+        ref_i = orc.calc_spec(wavs[i], win, hop, n_fft, None, msv.calc_mel_fb_default(srs[i], n_fft))
+        assert_db_vs_truth(mt.get_spec_db(i), ref_i, t, f"six rates track {i}")
     for i in range(6):
         rgb = mt.get_spec_image(i, 100.0, 500).reshape(500, -1, 3)
         dmx, frac = assert_pixels_close(rgb, imgs[i], f"track {i}")
