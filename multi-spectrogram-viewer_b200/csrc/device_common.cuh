@@ -111,6 +111,8 @@ struct RenderLaunch {
     int px, py;            // output tile
     int fc;                // frames per chunk
     int rv_max;            // grey rows a tile may need
+    int rv_cols, rv_rows;  // tensor-core path: widest column window of the launch, row tiles of 128
+    int debug;             // tensor-core path: print per-phase cycle counts of CTA 0 (SGX_K3_TC_PROF)
 };
 
 } // namespace sgx

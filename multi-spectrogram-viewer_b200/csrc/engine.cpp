@@ -632,7 +632,7 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
             size_t b = a + 1;
             while (b < items.size() && items[b].T == items[a].T && items[b].height == items[a].height &&
                    items[b].nwidth == items[a].nwidth) ++b;
-            const RenderTiling tl = plan_render_tiles(items[a].T, items[a].height, items[a].nwidth, (int)nheight);
+            const RenderTiling tl = plan_render_tiles(items[a].T, items[a].height, items[a].nwidth, (int)nheight, true);
             int max_cols = 0;
             for (size_t c = a; c < b; ++c) max_cols = std::max(max_cols, items[c].cols);
             for (size_t c = a; c < b; c += 65535) { // gridDim.z limit

@@ -16,6 +16,7 @@
 
 #include "device_common.cuh"
 #include "kernels.h"
+#include "render_device.cuh"
 
 namespace sgx {
 
@@ -147,8 +148,6 @@ __device__ __forceinline__ float clamp_pos(float v)
     return v < 0.0f ? 0.0f : (v > 3.4028235e38f ? 3.4028235e38f : v);
 }
 
-// the same clamp for values that cannot be NaN (sums of finite products): branch-free
-__device__ __forceinline__ float clamp_fin(float v) { return fminf(fmaxf(v, 0.0f), 3.4028235e38f); }
 
 // display.rs:24-42 convert_grey_to_color; cm = colour map as floats in shared memory
 __device__ __forceinline__ uchar4 grey_to_color(float x, const float *cm)
@@ -307,37 +306,6 @@ __host__ __device__ constexpr float fp_max_ratio(int taps) { return taps <= 8 ? 
 __host__ __device__ constexpr size_t fp_smem(int tv, int th)
 {
     return (size_t)(fp_cap(tv) * fp_cap(th) + fp_cap(th) * kFpTP) * sizeof(float);
-}
-
-// display.rs:24-42 with the colour map stored per channel as (a + 0.5, b - a) for the stops a = stop i,
-// b = stop i+1:  round(ratio*b + (1-ratio)*a) = floor(a + 0.5 + ratio*(b - a)), one FMA and one
-// conversion per channel.  The single rounding of the FMA can differ from the reference's three only when
-// the exact value lies within ~3e-5 of a rounding boundary (about 1 byte in 10^4, by 1 LSB).
-// The table lives in constant memory, as floats: {r.a, r.d, g.a, g.d} {b.a, b.d, -, -} per segment.  An indexed constant
-// load replays once per DISTINCT index in the warp (neighbouring pixels of a row mostly share one or two segments) and
-// does not touch the shared-memory / L1 data pipe that bounds the render kernels (C5 K3 3.92 -> 3.69 ms against a
-// 16-byte shared-memory entry per pixel, which was a sixth of the kernel's wavefronts).
-struct CmSeg { float4 rg, b; };
-__constant__ CmSeg kCmConst[9] = {
-#define SGX_SEG(r0, g0, b0, r1, g1, b1) {{r0 + 0.5f, (float)(r1 - r0), g0 + 0.5f, (float)(g1 - g0)}, {b0 + 0.5f, (float)(b1 - b0), 0.0f, 0.0f}}
-    SGX_SEG(0, 0, 4, 27, 12, 65), SGX_SEG(27, 12, 65, 74, 12, 107), SGX_SEG(74, 12, 107, 120, 28, 109),
-    SGX_SEG(120, 28, 109, 165, 44, 96), SGX_SEG(165, 44, 96, 207, 68, 70), SGX_SEG(207, 68, 70, 237, 105, 37),
-    SGX_SEG(237, 105, 37, 251, 155, 6), SGX_SEG(251, 155, 6, 247, 209, 61), SGX_SEG(247, 209, 61, 252, 255, 164)
-#undef SGX_SEG
-};
-__device__ __forceinline__ unsigned grey_to_rgba_const(float x)
-{
-    const float position = __fmul_rn(10.0f, x);
-    const float fl = floorf(position);
-    const int idx = min(__float2int_rz(fl), 8);
-    const float ratio = __fsub_rn(position, fl);
-    const float4 rg = kCmConst[idx].rg;
-    const float4 b = kCmConst[idx].b;
-    const unsigned cr = __float2uint_rd(fmaf(ratio, rg.y, rg.x));
-    const unsigned cg = __float2uint_rd(fmaf(ratio, rg.w, rg.z));
-    const unsigned cb = __float2uint_rd(fmaf(ratio, b.y, b.x));
-    const unsigned px = cr | (cg << 8) | (cb << 16) | 0xff000000u;
-    return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
 }
 
 // (packed FP32 pairs -- FFMA2 -- in the two tap loops were measured and change nothing, 3.905 vs 3.923 ms: the kernel is
@@ -811,10 +779,24 @@ cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_majo
     return cudaGetLastError();
 }
 
-RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight)
+RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight, bool from_db)
 {
     // fast path: at most 8 / 16 taps per output index on each axis (same f32 ratio the tap tables use)
     const float rhf = (float)width / (float)nwidth, rvf = (float)height / (float)nheight;
+    // tensor-core path (render_tc_kernel.cu): both axes in the 8-tap class, dB input, and a tile whose operands fit in
+    // shared memory -- 128 output rows need kv grey rows, nx output columns need nf source frames
+    // Measured on B200 (C5): 8.3 ms per step against 3.7 ms of the FP32 path -- see the header of render_tc_kernel.cu --
+    // so it is an evaluated alternative, selected with SGX_K3_TC=1.
+    static const bool tc_on = getenv("SGX_K3_TC") && atoi(getenv("SGX_K3_TC")) == 1;
+    if (from_db && tc_on && rhf < fp_max_ratio(8) && rvf < fp_max_ratio(8) && nheight >= 64 && nwidth >= 64) {
+        const float sv = rvf < 1.0f ? 1.0f : rvf, sh = rhf < 1.0f ? 1.0f : rhf;
+        const int kv = ((int)std::ceil(127.0 * rvf + 6.0 * sv) + 3 + 7) & ~7;
+        for (int nx : {64, 48, 32}) {
+            const int nf = ((int)std::ceil((nx - 1) * (double)rhf + 6.0 * sh) + 3 + 15) & ~15;
+            const size_t smem = render_tc_smem(kv, nf, nx);
+            if (nf <= 96 && smem + 1024 <= (size_t)227 * 1024) return RenderTiling{nx, 128, nf, kv, smem, 2};
+        }
+    }
     if (rhf < fp_max_ratio(16) && rvf < fp_max_ratio(16)) {
         const int th = rhf < fp_max_ratio(8) ? 8 : 16, tv = rvf < fp_max_ratio(8) ? 8 : 16;
         RenderTiling t{};
@@ -889,6 +871,11 @@ cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight
                           int fast, cudaStream_t s)
 {
     if (L.n_tracks <= 0 || max_nwidth <= 0 || max_nheight <= 0) return cudaSuccess;
+    if (fast == 2) { // tensor-core path
+        RenderLaunch T = L;
+        T.rv_cols = max_nwidth; T.rv_rows = (max_nheight + 127) / 128;
+        return launch_render_tc(T, smem_bytes, s);
+    }
     if (fast == 1) { // wide path: tile L.px x L.py, capacities in L.fc / L.rv_max
         dim3 grid((max_nwidth + L.px - 1) / L.px, (max_nheight + L.py - 1) / L.py, L.n_tracks);
         cudaError_t err = cudaErrorInvalidValue;

@@ -70,7 +70,7 @@ def assert_db_vs_truth(got_db, ref_db, truth_db, what="", db_range=120.0):
             break
         # the RMS measures the noise level itself; the upper quantile looks at the tail but leaves out the ~20 worst
         # bins of the band (the maximum of a heteroscedastic error over a few hundred bins is decided by one bin)
-        q = 1.0 - max(1e-3, 20.0 / float(band.sum()))
+        q = min(1.0, max(0.5, 1.0 - max(1e-3, 20.0 / float(band.sum()))))
         for name, stat in (("rms", lambda e: float(np.sqrt(np.mean(e[band] ** 2)))), (f"p{100 * q:.1f}", lambda e: float(np.quantile(e[band], q)))):
             g, r = stat(e_gpu), stat(e_ref)
             report.append((lo, hi, name, g, r))

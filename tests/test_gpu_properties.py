@@ -125,6 +125,44 @@ def test_many_zoom_levels_do_not_invalidate_axis_tables(msv):
         fresh.close()
 
 
+def test_tensor_core_render_path_parity(orc):
+    """The tcgen05 render kernel (SGX_K3_TC=1, csrc/render_tc_kernel.cu: both Lanczos passes as 3xTF32 MMAs with TMEM
+    accumulators) must meet the pixel tolerance of the FP32 path: +-1 LSB on < 1 % of the bytes against the oracle, for
+    RGB and RGBA, several sample rates (tile shapes) and a column window that is not a multiple of the tile width."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import msv_b200 as msv, oracle_binding, synth
+from parity import assert_pixels_close, assert_range_close
+orc = oracle_binding.load()
+srs = [8000, 16000, 22050, 44100, 48000]
+wavs = [synth.derive_track(synth.base_clip(int(3.7 * sr) + 13, sr, seed=sr), i) for i, sr in enumerate(srs)]
+params = [orc.track_params(sr) for sr in srs]
+fbs = [orc.calc_mel_fb_default(sr, p[2]) for sr, p in zip(srs, params)]
+wins = [orc.calc_window(p[0], p[2]) for p in params]
+for ch in (3, 4):
+    imgs, mx, mn = orc.pipeline(wavs, srs, params, wins, fbs, channels=ch, px_per_sec=100.0, nheight=500)
+    n0 = msv.kernel_launch_count()
+    mt = msv.MultiTrack()
+    mt.add_tracks_pcm(list(range(len(srs))), wavs, srs)
+    assert_range_close((mt.get_max_db(), mt.get_min_db()), (mx, mn), what="tc range")
+    got = mt.get_spec_images(list(range(len(srs))), 100.0, 500, ch)
+    for i, g in enumerate(got):
+        d, frac = assert_pixels_close(g.reshape(imgs[i].shape), imgs[i], f"tc track {i} ch {ch}")
+        print(f"tc sr={srs[i]} ch={ch}: max diff {d}, mismatching bytes {frac:.2e}")
+    mt.close()
+print("K3 TC OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SGX_K3_TC="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "K3 TC OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_warp_pair_kernel_at_n_fft_2048_parity(orc):
     """n_fft = 2048 has two kernels: the block kernel (default, exercised by every other test) and the
     warp-per-frame-pair one (SGX_K1W2=1, csrc/stft_warp2_kernel.cu).  The alternative must meet the same
