@@ -269,7 +269,11 @@ void MultiTrack::reduce_local()
     uint32_t msr = 0;
     for (auto &kv : tracks_) msr = std::max(msr, kv.second.sr);
     if (msr != max_sr_) { max_sr_ = msr; changed_acc_ = true; }
-    SGX_CUDA(launch_range_reduce(slots_.p, n_slots_, d_local_.p, (float)max_sr_, max_sec_, stream_));
+    // a lone handle whose caller waits for `changed` commits in the same launch (one launch less per add / remove)
+    const bool fuse = fuse_commit_ && !comm_;
+    SGX_CUDA(launch_range_reduce(slots_.p, n_slots_, d_local_.p, (float)max_sr_, max_sec_, set_.db_range, fuse ? d_state_.p : nullptr, stream_));
+    committed_in_reduce_ = fuse;
+    if (fuse) pending_ = true;
 }
 
 void MultiTrack::attach_comm(NcclComm comm, int rank, int world, bool owned)
@@ -330,11 +334,13 @@ uint32_t MultiTrack::effective_max_sr() const { return global_max_sr_ ? std::max
 bool MultiTrack::add_tracks(const std::vector<size_t> &ids, std::vector<PcmSource> &srcs, bool want_changed, bool sliced)
 {
     if (ids.size() != srcs.size()) throw Error(SGX_ERR_BAD_ARG, "id_list and track list differ in length");
+    fuse_commit_ = want_changed;
     if (sliced) analyse(ids, srcs); else analyse_owned(ids, srcs);
+    fuse_commit_ = false;
     exchange();
     // without a communicator and without a waiting caller the range stays uncommitted: a driver that shards by its
     // own means all-reduces range_device_ptr() in-stream and calls commit_range_device()
-    if (want_changed || comm_) commit();
+    if ((want_changed || comm_) && !committed_in_reduce_) commit();
     if (!want_changed) return false;
     return synchronize();
 }
@@ -497,9 +503,11 @@ void MultiTrack::analyse(const std::vector<size_t> &ids, std::vector<PcmSource> 
 
 bool MultiTrack::remove_track(size_t id, bool want_changed)
 {
+    fuse_commit_ = want_changed;
     drop(id);
+    fuse_commit_ = false;
     exchange();
-    if (want_changed || comm_) commit();
+    if ((want_changed || comm_) && !committed_in_reduce_) commit();
     if (!want_changed) return false;
     return synchronize();
 }
@@ -618,23 +626,32 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
         descs.push_back(r);
     }
     if (!descs.empty()) {
-        // tracks with identical geometry share a launch
-        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-            return std::tie(a.T, a.height, a.nwidth) < std::tie(b.T, b.height, b.nwidth);
-        });
+        // Tracks that can share a launch sit next to each other: the FP32 fast paths read every geometry value from the
+        // track's own descriptor, so all tracks of one tap class go into ONE launch whatever their length, sample rate or
+        // mel height (six rates x six geometries: one render launch instead of six); the wide, general and tensor-core
+        // paths size their tiles for a geometry and take identical geometries only.
+        struct Group { std::tuple<int, int, int, int> key; RenderTiling tl; };
+        std::vector<Group> plan(items.size());
+        for (size_t i = 0; i < items.size(); ++i) {
+            const RenderTiling tl = plan_render_tiles(items[i].T, items[i].height, items[i].nwidth, (int)nheight, true);
+            plan[i].tl = tl;
+            plan[i].key = tl.fast >= 100 ? std::make_tuple(tl.fast, 0, 0, 0) : std::make_tuple(tl.fast, items[i].T, items[i].height, items[i].nwidth);
+        }
+        std::vector<size_t> order(items.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return plan[x].key < plan[y].key; });
         std::vector<RenderTrack> sorted;
-        for (const Item &it : items) sorted.push_back(descs[it.idx]);
+        for (size_t i : order) sorted.push_back(descs[items[i].idx]);
         d_render_.ensure(sorted.size());
         SGX_CUDA(cudaMemcpyAsync(d_render_.p, sorted.data(), sizeof(RenderTrack) * sorted.size(), cudaMemcpyHostToDevice, stream_));
         if (profiling_) SGX_CUDA(cudaEventRecord(ev_[2], stream_));
         size_t a = 0;
-        while (a < items.size()) {
+        while (a < order.size()) {
             size_t b = a + 1;
-            while (b < items.size() && items[b].T == items[a].T && items[b].height == items[a].height &&
-                   items[b].nwidth == items[a].nwidth) ++b;
-            const RenderTiling tl = plan_render_tiles(items[a].T, items[a].height, items[a].nwidth, (int)nheight, true);
+            while (b < order.size() && plan[order[b]].key == plan[order[a]].key) ++b;
+            const RenderTiling tl = plan[order[a]].tl;
             int max_cols = 0;
-            for (size_t c = a; c < b; ++c) max_cols = std::max(max_cols, items[c].cols);
+            for (size_t c = a; c < b; ++c) max_cols = std::max(max_cols, items[order[c]].cols);
             for (size_t c = a; c < b; c += 65535) { // gridDim.z limit
                 RenderLaunch L{};
                 L.tracks = d_render_.p + c; L.n_tracks = (int)std::min<size_t>(65535, b - c);

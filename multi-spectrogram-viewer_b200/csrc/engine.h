@@ -208,6 +208,7 @@ private:
     int rank_ = 0, world_ = 1;
     float global_max_sec_ = 0.0f;
     bool global_sr_fixed_ = false;
+    bool fuse_commit_ = false, committed_in_reduce_ = false; // the range commit rides on the reduce launch (lone handle)
     float max_db_, min_db_;
     float max_sec_ = 0.0f;
     size_t id_max_sec_ = 0;

@@ -52,8 +52,9 @@ cudaError_t launch_range_init(unsigned *slots, int n_slots, cudaStream_t s);
 // resets the range slot of every track of a K1 descriptor array to the identity of the reduce
 cudaError_t launch_range_reset(const StftTrack *descs, int n, cudaStream_t s);
 // reduces slots [n][2] -> local {max, -min, max_sr, max_sec} (the last two are host metadata passed through)
+// commit_state != nullptr: launch_range_commit's work is done by the same launch (no exchange in between)
 cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *local_max_negmin, float max_sr,
-                                float max_sec, cudaStream_t s);
+                                float max_sec, float db_range, float *commit_state, cudaStream_t s);
 // {max, -min, max_sr, max_sec} -> state {max_db, min_db, changed, max_sr, max_sec}: the clamps of lib.rs:208-209
 // and the sticky 1e-3 change detection of lib.rs:210-218, all on the device
 cudaError_t launch_range_commit(const float *max_negmin, float db_range, float *state,

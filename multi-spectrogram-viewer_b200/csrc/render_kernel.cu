@@ -43,7 +43,11 @@ __global__ void range_reset_kernel(const StftTrack *__restrict__ descs, int n)
     }
 }
 
-__global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, float *out, float max_sr, float max_sec)
+__device__ __forceinline__ void range_commit_dev(const float *max_negmin, float db_range, float *state);
+
+// state != nullptr: the commit of lib.rs:208-218 follows in the same launch (single handle, no exchange in between)
+__global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, float *out, float max_sr, float max_sec,
+                                    float db_range, float *state)
 {
     __shared__ float smax[32], smin[32];
     float mx = -INFINITY, mn = INFINITY;
@@ -63,6 +67,7 @@ __global__ void range_reduce_kernel(const unsigned *__restrict__ slots, int n, f
         out[1] = -mn;
         out[2] = max_sr;  // lib.rs:220-224 and lib.rs:178-182: metadata of this handle's tracks, so that one
         out[3] = max_sec; // exchange serves everything update_spec_greys needs from the other shards
+        if (state != nullptr) range_commit_dev(out, db_range, state);
     }
 }
 
@@ -73,7 +78,7 @@ __device__ __forceinline__ bool abs_diff_ne(float a, float b, float eps)
     return !(d <= eps);
 }
 
-__global__ void range_commit_kernel(const float *__restrict__ max_negmin, float db_range, float *state)
+__device__ __forceinline__ void range_commit_dev(const float *max_negmin, float db_range, float *state)
 {
     // lib.rs:208-209: max = max.min(0.); min = min.max(max - db_range)
     const float mx = fminf(max_negmin[0], 0.0f);
@@ -82,6 +87,11 @@ __global__ void range_commit_kernel(const float *__restrict__ max_negmin, float 
     if (abs_diff_ne(state[0], mx, 1e-3f)) { state[0] = mx; state[2] = 1.0f; }
     if (abs_diff_ne(state[1], mn, 1e-3f)) { state[1] = mn; state[2] = 1.0f; }
     state[3] = max_negmin[2]; state[4] = max_negmin[3]; // max_sr, max_sec over all shards
+}
+
+__global__ void range_commit_kernel(const float *__restrict__ max_negmin, float db_range, float *state)
+{
+    range_commit_dev(max_negmin, db_range, state);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -754,9 +764,10 @@ cudaError_t launch_range_reset(const StftTrack *descs, int n, cudaStream_t s)
     count_launch();
     return cudaGetLastError();
 }
-cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *out, float max_sr, float max_sec, cudaStream_t s)
+cudaError_t launch_range_reduce(const unsigned *slots, int n_slots, float *out, float max_sr, float max_sec, float db_range,
+                                float *commit_state, cudaStream_t s)
 {
-    range_reduce_kernel<<<1, 256, 0, s>>>(slots, n_slots, out, max_sr, max_sec);
+    range_reduce_kernel<<<1, 256, 0, s>>>(slots, n_slots, out, max_sr, max_sec, db_range, commit_state);
     count_launch();
     return cudaGetLastError();
 }
