@@ -635,7 +635,9 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
         for (size_t i = 0; i < items.size(); ++i) {
             const RenderTiling tl = plan_render_tiles(items[i].T, items[i].height, items[i].nwidth, (int)nheight, true);
             plan[i].tl = tl;
-            plan[i].key = tl.fast >= 100 ? std::make_tuple(tl.fast, 0, 0, 0) : std::make_tuple(tl.fast, items[i].T, items[i].height, items[i].nwidth);
+            plan[i].key = tl.fast >= 100 ? std::make_tuple(tl.fast, 0, 0, 0)
+                          : tl.fast == 3 ? std::make_tuple(3, 0, 0, 0) // sliding-window path: one launch, sized for the tallest source window
+                                         : std::make_tuple(tl.fast, items[i].T, items[i].height, items[i].nwidth);
         }
         std::vector<size_t> order(items.size());
         for (size_t i = 0; i < order.size(); ++i) order[i] = i;
@@ -649,9 +651,15 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
         while (a < order.size()) {
             size_t b = a + 1;
             while (b < order.size() && plan[order[b]].key == plan[order[a]].key) ++b;
-            const RenderTiling tl = plan[order[a]].tl;
+            RenderTiling tl = plan[order[a]].tl;
             int max_cols = 0;
-            for (size_t c = a; c < b; ++c) max_cols = std::max(max_cols, items[order[c]].cols);
+            for (size_t c = a; c < b; ++c) {
+                max_cols = std::max(max_cols, items[order[c]].cols);
+                if (tl.fast == 3) { // capacities of the group = those of its most demanding track
+                    tl.rv_max = std::max(tl.rv_max, plan[order[c]].tl.rv_max);
+                    tl.smem_bytes = std::max(tl.smem_bytes, plan[order[c]].tl.smem_bytes);
+                }
+            }
             for (size_t c = a; c < b; c += 65535) { // gridDim.z limit
                 RenderLaunch L{};
                 L.tracks = d_render_.p + c; L.n_tracks = (int)std::min<size_t>(65535, b - c);

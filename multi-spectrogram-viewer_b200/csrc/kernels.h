@@ -65,12 +65,16 @@ struct AxisTable { int *left, *cnt; float *sum, *w; int taps; int n_in, n_out; b
 uint32_t lanczos3_max_taps(uint32_t n_in, uint32_t n_out);
 cudaError_t launch_build_axis_table(int n_in, int n_out, int taps, bool tap_major, int *left,
                                     int *cnt, float *sum, float *w, cudaStream_t s);
-// fast: 0 general kernel, 1 wide path, 2 tensor-core path (render_tc_kernel.cu), TV * 100 + TH fast FP32 path
+// fast: 0 general kernel, 1 wide path, 2 tensor-core path (render_tc_kernel.cu), 3 sliding-window path
+// (render_slide_kernel.cu), TV * 100 + TH fast FP32 path
 struct RenderTiling { int px, py, fc, rv_max; size_t smem_bytes; int fast; };
 RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight, bool from_db = false);
 // the tcgen05 path: tiles of 128 rows x L.px columns, L.fc source frames, L.rv_max grey rows per tile
 size_t render_tc_smem(int kv, int nf, int nx);
 cudaError_t launch_render_tc(const RenderLaunch &launch, size_t smem_bytes, cudaStream_t s);
+// the sliding-window path: tiles of 120 x 64 pixels, L.fc source frames (multiple of 32), L.rv_max grey rows per tile
+bool render_slide_plan(int width, int height, int nwidth, int nheight, RenderTiling *out);
+cudaError_t launch_render_slide(const RenderLaunch &launch, int max_nwidth, int max_nheight, size_t smem_bytes, cudaStream_t s);
 cudaError_t launch_render(const RenderLaunch &launch, int max_nwidth, int max_nheight,
                           size_t smem_bytes, int fast, cudaStream_t s);
 

@@ -40,5 +40,84 @@ __device__ __forceinline__ unsigned grey_to_rgba_const(float x)
     return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
 }
 
+// The same function without conversion instructions (F2I / FRND run on the quarter-rate XU pipe: five per pixel were
+// 1.0 ms of XU time per C5 step).  For 0 <= v < 2^23, v + 2^23 rounded towards minus infinity is 2^23 + floor(v) exactly,
+// so the integer sits in the low mantissa bits: floor(position) for the segment index (position <= ~12) and the three
+// channel bytes.  Bit-identical to grey_to_rgba_const for every finite x >= 0 (tools/check_colormap_fadd.cpp).
+__device__ __forceinline__ unsigned grey_to_rgba_fadd(float x)
+{
+    const float kMagic = 8388608.0f; // 2^23
+    const float position = __fmul_rn(10.0f, fminf(x, 1.5f)); // x >= 1 is the last colour already; keeps position < 16
+    const float tf = __fadd_rd(position, kMagic);
+    const unsigned ti = __float_as_uint(tf) & 0xfu;       // floor(position), 0 .. 15
+    const float fl = __fsub_rn(tf, kMagic);               // exact
+    const int idx = min((int)ti, 8);
+    const float ratio = __fsub_rn(position, fl);
+    const float4 rg = kCmConst[idx].rg;
+    const float4 b = kCmConst[idx].b;
+    const unsigned cr = __float_as_uint(__fadd_rd(fmaf(ratio, rg.y, rg.x), kMagic));
+    const unsigned cg = __float_as_uint(__fadd_rd(fmaf(ratio, rg.w, rg.z), kMagic));
+    const unsigned cb = __float_as_uint(__fadd_rd(fmaf(ratio, b.y, b.x), kMagic));
+    // bytes: [0] = cr.b0, [1] = cg.b0, [2] = cb.b0, [3] = 0xff
+    const unsigned px = __byte_perm(__byte_perm(cr, cg, 0x0040), cb, 0x7410) | 0xff000000u;
+    return ti < 9u ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
+}
+
+// The leanest form, used by the sliding-window kernel.  With position = i + ratio (ratio = position - floor(position) is
+// exact in f32), ratio * d + (a + 0.5) and position * d + (a + 0.5 - i d) are the SAME real number, and a + 0.5 - i d
+// is a small multiple of 0.5, exact in f32: one FMA per channel straight from `position`, bit-identical to the two forms
+// above, with neither floor nor ratio computed.  A tenth table entry (d = 0) returns the last colour for position >= 9.
+struct CmPos { float4 rg, b; };
+__constant__ CmPos kCmPos[10] = {
+#define SGX_SEGP(i, r0, g0, b0, r1, g1, b1)                                                                              \
+    {{r0 + 0.5f - (float)(i) * (float)(r1 - r0), (float)(r1 - r0), g0 + 0.5f - (float)(i) * (float)(g1 - g0), (float)(g1 - g0)}, \
+     {b0 + 0.5f - (float)(i) * (float)(b1 - b0), (float)(b1 - b0), 0.0f, 0.0f}}
+    SGX_SEGP(0, 0, 0, 4, 27, 12, 65), SGX_SEGP(1, 27, 12, 65, 74, 12, 107), SGX_SEGP(2, 74, 12, 107, 120, 28, 109),
+    SGX_SEGP(3, 120, 28, 109, 165, 44, 96), SGX_SEGP(4, 165, 44, 96, 207, 68, 70), SGX_SEGP(5, 207, 68, 70, 237, 105, 37),
+    SGX_SEGP(6, 237, 105, 37, 251, 155, 6), SGX_SEGP(7, 251, 155, 6, 247, 209, 61), SGX_SEGP(8, 247, 209, 61, 252, 255, 164),
+    SGX_SEGP(0, 252, 255, 164, 252, 255, 164)
+#undef SGX_SEGP
+};
+// t: the un-clamped sum of the last resampling pass.  __saturatef is the clamp at 0 of image's resize; values above 1
+// all map to the last colour, as do 1 and everything from 0.9 on (display.rs:31), so clipping them to 1 changes nothing.
+__device__ __forceinline__ unsigned grey_to_rgba_sat(float t)
+{
+    const float kMagic = 8388608.0f; // 2^23
+    const float position = __fmul_rn(10.0f, __saturatef(t)); // <= 10
+    const unsigned ti = __float_as_uint(__fadd_rd(position, kMagic)) & 0xfu; // floor(position), 0 .. 15
+    const int idx = min((int)ti, 9);
+    const float4 rg = kCmPos[idx].rg;
+    const float4 b = kCmPos[idx].b;
+    const unsigned cr = __float_as_uint(__fadd_rd(fmaf(position, rg.y, rg.x), kMagic));
+    const unsigned cg = __float_as_uint(__fadd_rd(fmaf(position, rg.w, rg.z), kMagic));
+    const unsigned cb = __float_as_uint(__fadd_rd(fmaf(position, b.y, b.x), kMagic));
+    return __byte_perm(__byte_perm(cr, cg, 0x0040), cb, 0x7410) | 0xff000000u; // [0] = cr.b0, [1] = cg.b0, [2] = cb.b0, [3] = 0xff
+}
+
+// grey_to_rgba_sat for a lane that walks along an image row: neighbouring pixels mostly fall into the same colour segment,
+// so the segment's six constants stay in registers and are re-loaded (predicated, per lane) only when the segment
+// changes.  An indexed constant load costs one request per DISTINCT index among the lanes that execute it: with the
+// lanes of a warp on 32 different rows that was ~3 requests per load and pixel, and the indexed constant cache bounded the
+// colour phase (ncu: idc request cycles ~100 % during it); lanes whose segment did not change make no request.
+struct CmCache { float4 rg; float2 b; int idx; };
+__device__ __forceinline__ void cm_cache_init(CmCache &c) { c.idx = -1; c.rg = make_float4(0.f, 0.f, 0.f, 0.f); c.b = make_float2(0.f, 0.f); }
+__device__ __forceinline__ unsigned grey_to_rgba_cached(float t, CmCache &c)
+{
+    const float kMagic = 8388608.0f; // 2^23
+    const float position = __fmul_rn(10.0f, __saturatef(t)); // <= 10
+    const unsigned ti = __float_as_uint(__fadd_rd(position, kMagic)) & 0xfu; // floor(position), 0 .. 10
+    const int idx = min((int)ti, 9);
+    if (idx != c.idx) {
+        c.rg = kCmPos[idx].rg;
+        const float4 b = kCmPos[idx].b;
+        c.b = make_float2(b.x, b.y);
+        c.idx = idx;
+    }
+    const unsigned cr = __float_as_uint(__fadd_rd(fmaf(position, c.rg.y, c.rg.x), kMagic));
+    const unsigned cg = __float_as_uint(__fadd_rd(fmaf(position, c.rg.w, c.rg.z), kMagic));
+    const unsigned cb = __float_as_uint(__fadd_rd(fmaf(position, c.b.y, c.b.x), kMagic));
+    return __byte_perm(__byte_perm(cr, cg, 0x0040), cb, 0x7410) | 0xff000000u;
+}
+
 } // namespace
 } // namespace sgx

@@ -808,6 +808,12 @@ RenderTiling plan_render_tiles(int width, int height, int nwidth, int nheight, b
             if (nf <= 96 && smem + 1024 <= (size_t)227 * 1024) return RenderTiling{nx, 128, nf, kv, smem, 2};
         }
     }
+    // sliding-window path (render_slide_kernel.cu): both axes in the 8-tap class; SGX_K3_SLIDE=0 keeps render_fast_kernel
+    static const bool slide_on = !(getenv("SGX_K3_SLIDE") && atoi(getenv("SGX_K3_SLIDE")) == 0);
+    if (slide_on) {
+        RenderTiling t{};
+        if (render_slide_plan(width, height, nwidth, nheight, &t)) return t;
+    }
     if (rhf < fp_max_ratio(16) && rvf < fp_max_ratio(16)) {
         const int th = rhf < fp_max_ratio(8) ? 8 : 16, tv = rvf < fp_max_ratio(8) ? 8 : 16;
         RenderTiling t{};
@@ -887,6 +893,7 @@ cudaError_t launch_render(const RenderLaunch &L, int max_nwidth, int max_nheight
         T.rv_cols = max_nwidth; T.rv_rows = (max_nheight + 127) / 128;
         return launch_render_tc(T, smem_bytes, s);
     }
+    if (fast == 3) return launch_render_slide(L, max_nwidth, max_nheight, smem_bytes, s);
     if (fast == 1) { // wide path: tile L.px x L.py, capacities in L.fc / L.rv_max
         dim3 grid((max_nwidth + L.px - 1) / L.px, (max_nheight + L.py - 1) / L.py, L.n_tracks);
         cudaError_t err = cudaErrorInvalidValue;

@@ -163,6 +163,52 @@ print("K3 TC OK")
     assert r.returncode == 0 and "K3 TC OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_sliding_window_render_kernel_matches_the_tile_kernel_bit_for_bit():
+    """The 8-tap geometry class has two FP32 render kernels: the sliding-window one (default,
+    csrc/render_slide_kernel.cu) and render_fast_kernel (SGX_K3_SLIDE=0).  They apply the same operations in the same
+    order, so every pixel must be IDENTICAL -- over RGB and RGBA, widths that are and are not multiples of 4 (128-bit
+    and scalar store paths), horizontal ratios at and below 1 (unit-step and general column blocks), heights that
+    are not a multiple of the tile, and several sample rates in one call (one launch over mixed geometries).  The kernel
+    is chosen per process, so both run in children."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import msv_b200 as msv, synth
+srs = [8000, 16000, 22050, 44100, 48000]
+wavs = [synth.derive_track(synth.base_clip(int(3.3 * sr) + 17 * i + 5, sr, seed=sr), i) for i, sr in enumerate(srs)]
+out = {}
+mt = msv.MultiTrack()
+mt.add_tracks_pcm(list(range(len(srs))), wavs, srs)
+for ch in (3, 4):
+    for pps, nh in ((100.0, 500), (100.0, 333), (173.0, 257), (250.0, 64), (97.0, 1000)):
+        for i, g in enumerate(mt.get_spec_images(list(range(len(srs))), pps, nh, ch)):
+            out[f"{ch}_{pps}_{nh}_{i}"] = np.asarray(g).copy()
+n1 = msv.kernel_launch_count()
+mt.close()
+np.savez(sys.argv[1], **out)
+print("K3 AB OK", len(out))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = {}
+    with tempfile.TemporaryDirectory() as td:
+        for name, flag in (("slide", "1"), ("tile", "0")):
+            path = os.path.join(td, name + ".npz")
+            env = dict(os.environ, SGX_K3_SLIDE=flag)
+            r = subprocess.run([sys.executable, "-c", code, path], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0 and "K3 AB OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+            with np.load(path) as z:
+                got[name] = {k: z[k] for k in z.files}
+    assert got["slide"].keys() == got["tile"].keys() and len(got["slide"]) == 50
+    for k in got["slide"]:
+        a, b = got["slide"][k], got["tile"][k]
+        assert a.shape == b.shape and np.array_equal(a, b), f"{k}: {int((a != b).sum())} of {a.size} bytes differ"
+
+
 def test_warp_pair_kernel_at_n_fft_2048_parity(orc):
     """n_fft = 2048 has two kernels: the block kernel (default, exercised by every other test) and the
     warp-per-frame-pair one (SGX_K1W2=1, csrc/stft_warp2_kernel.cu).  The alternative must meet the same
