@@ -12,10 +12,10 @@ import json
 try:
     d=json.loads(open("gpurun_out/bench_n$N.log").read().strip().splitlines()[-1]); r=d["roofline_step"]; e=d["e2e"]
     print("n=$N value %.0f step %.3f ms k1 %.3f k3 %.3f launches %d" % (d["value"], d["ms_per_step"], r["k1_ms"], r["k3_ms"], d["gpu_launches"]))
-    print("e2e %.0f (%.1f ms)  pipelined %.0f (%.1f ms)  int16 pipelined %.0f" % (e["value"], e["ms_per_step"], e["pipelined"]["value"], e["pipelined"]["ms_per_step"], e["int16_pcm_pipelined"]["value"]))
-    print("link", e["per_rank_link_gbs"], e["pipelined"]["per_rank_link_gbs"])
+    print("e2e %.0f (%.1f ms)  one batch at a time %.0f (%.1f ms)  int16 pipelined %.0f" % (e["value"], e["ms_per_step"], e["one_batch_at_a_time"]["value"], e["one_batch_at_a_time"]["ms_per_step"], e["int16_pcm_pipelined"]["value"]))
+    print("link", e["per_rank_link_gbs"], e["one_batch_at_a_time"]["per_rank_link_gbs"])
 except Exception as ex:
     print("bench parse failed", ex); print(open("gpurun_out/bench_n$N.err").read()[-1500:])
 PY
 timeout 900 ./benches/bench --c5 $((32 * N)) 600 2>&1 | tail -2
-[ -n "$SKIP_REF" ] || timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.log 2>&1; echo "ref exit $?"; tail -c 400 gpurun_out/bench_ref_n$N.log
+if [ -z "$SKIP_REF" ]; then timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.log 2>&1; echo "ref exit $?"; tail -c 400 gpurun_out/bench_ref_n$N.log; fi
