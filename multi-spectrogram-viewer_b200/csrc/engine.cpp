@@ -677,6 +677,10 @@ void MultiTrack::render(const std::vector<size_t> &ids, float px_per_sec, uint32
 void MultiTrack::render_host(size_t id, float px_per_sec, uint32_t nheight, int channels, uint8_t *out, size_t need)
 {
     if (need == 0) return;
+    // the staging buffer must live on THIS engine's device: a multi-device handle enters with the caller's device current
+    // (found on 8 GPUs: allocated on device 0, written by a kernel on device 5 -- it only worked where NCCL had enabled
+    // peer access between the two)
+    SGX_CUDA(cudaSetDevice(device_));
     d_img_.ensure(need);
     uint8_t *outs[1] = {d_img_.p};
     size_t caps[1] = {need}, wr[1] = {0};
@@ -740,6 +744,7 @@ void MultiTrack::wait_images()
 
 void MultiTrack::set_profiling(bool on)
 {
+    SGX_CUDA(cudaSetDevice(device_));
     if (on && !ev_[0]) for (auto &e : ev_) SGX_CUDA(cudaEventCreate(&e));
     profiling_ = on;
     ev_valid_[0] = ev_valid_[1] = false;
@@ -747,6 +752,7 @@ void MultiTrack::set_profiling(bool on)
 
 void MultiTrack::stage_times(float *analysis_ms, float *render_ms)
 {
+    SGX_CUDA(cudaSetDevice(device_));
     SGX_CUDA(cudaStreamSynchronize(stream_));
     *analysis_ms = *render_ms = -1.0f;
     if (ev_valid_[0]) SGX_CUDA(cudaEventElapsedTime(analysis_ms, ev_[0], ev_[1]));
