@@ -20,9 +20,9 @@
 //      pixels leave through a per-warp staging tile as 128-bit stores (16 rows x 32 bytes per instruction).
 // Shared memory per CTA at the bench geometry (tile 120 x 64 pixels, 128 frames x 56 grey rows): G 29.6 KB (reused as the
 // pixel staging) + Tm 33.3 KB + tables 6.8 KB = 70 KB -> 3 CTAs per SM, 80 registers.
-// MEASURED (B200, C5, ms per step; profiles/r02_k3_slide_*): 3.54 against render_fast_kernel's 3.69 with 74 instead of 96
-// instructions per pixel and 0.43 instead of 0.81 shared-memory wavefronts per pixel.  The gain is small because the
-// kernel is no longer bound by one pipe: issue slots 57 % busy, L1/shared data pipe 72 % (a third of it the 32-byte
+// MEASURED (B200, C5, ms per step; profiles/r02_k3_slide_*): 3.54 against render_fast_kernel's 3.69 with 81 instead of 96
+// instructions per pixel and 0.6 instead of 0.8 shared-memory wavefronts per pixel.  The gain is small because the
+// kernel is no longer bound by one pipe: issue slots 59 % busy, L1/shared data pipe 73 % (a third of it the 32-byte
 // sectors of the global stores and the LDGSTS fill), and with 24 warps per SM the dependent FFMA2 chains and
 // shared-memory round trips are not fully hidden (stall reasons: short scoreboard 2.3, wait 2.2 per issue).
 // Arithmetic (order of the taps, normalised weights, clamps, colour map) is that of render_fast_kernel operation for
