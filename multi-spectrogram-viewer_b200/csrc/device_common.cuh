@@ -52,6 +52,7 @@ struct StftLaunch {
     int bank_floats;       // > 0: the CTA keeps the track's mel taps + descriptors in a region of its own
     int stereo_raw;        // raw-tile loader of the launch -- 1: f32 stereo tracks (tiles have room for the pairs), 2: int16 mono tracks, 0: none
     int warp2;             // > 0: tiles were planned for the warp-per-frame-pair kernel (n_fft = 2048) with that many warps
+    int warp1;             // > 0: tiles were planned for the warp-per-frame kernel (n_fft = 2048) with that many warps
     const float2 *tw;      // [h]      exp(-2 pi i j / h)
     const float2 *twr;     // twiddles of the Stockham passes, pass after pass, r-major (kernels.h make_fft_pass_tables)
     const float2 *split;   // [h/2+1]  (cos, sin)(k pi / h)                realfft.rs:88-93

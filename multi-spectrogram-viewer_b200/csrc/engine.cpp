@@ -110,7 +110,7 @@ static void fill_tables(TrackTables &tt, size_t win, size_t n_fft, const float *
         const size_t plane = cfg.generic ? 0 : cfg.fft_smem / sizeof(float) / (2 * (size_t)cfg.groups);
         // the warp kernel walks all blocks with one warp and reads magnitude PAIRS; the block kernel spreads them
         // over the warps of a group and reads vectors of cfg.vec frames
-        MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg, plane, cfg.warp2 ? 2 : cfg.vec);
+        MelBands mb = make_mel_bands(mel_fb, n_fft / 2 + 1, n_mel, tpg, plane, cfg.warp1 ? 1 : (cfg.warp2 ? 2 : cfg.vec));
         if (cfg.generic) mb.log2_split = 0;
         std::vector<int> meta(4 * n_mel, 0); // {lo, cnt, off, 0} per filter: one 16-byte load on the device
         for (size_t m = 0; m < n_mel; ++m) { meta[4 * m] = mb.lo[m]; meta[4 * m + 1] = mb.cnt[m]; meta[4 * m + 2] = mb.off[m]; }
@@ -484,7 +484,7 @@ void MultiTrack::analyse(const std::vector<size_t> &ids, std::vector<PcmSource> 
         L.mode = set_.freq_scale == SGX_FREQ_MEL ? MODE_MEL_DB : MODE_LIN_DB;
         L.frames_per_tile = g.tiling.frames_per_tile; L.staged = g.tiling.staged;
         L.tile_floats = g.tiling.tile_floats; L.bank_floats = g.tiling.bank_floats; L.tw = pl.tw.p; L.split = pl.split.p; L.twr = pl.twr.p;
-        L.stereo_raw = g.tiling.sample_floats == 2 ? 1 : (g.raw_loader ? 2 : 0); L.warp2 = g.tiling.warp2;
+        L.stereo_raw = g.tiling.sample_floats == 2 ? 1 : (g.raw_loader ? 2 : 0); L.warp2 = g.tiling.warp2; L.warp1 = g.tiling.warp1;
         if (!pipelined) { SGX_CUDA(launch_stft(pl.cfg, L, stream_)); continue; }
         for (size_t k = 0; k < g.count; ++k) {
             const size_t di = g.first + k;
@@ -866,7 +866,7 @@ StageOut stage_stft(int mode, const float *input, size_t n, size_t win, size_t h
     L.tracks = dd.p; L.n_tracks = 1;
     L.n_tiles = (int)(((size_t)T + tl.frames_per_tile - 1) / tl.frames_per_tile);
     L.mode = mode; L.frames_per_tile = tl.frames_per_tile; L.staged = tl.staged; L.tile_floats = tl.tile_floats;
-    L.bank_floats = tl.bank_floats; L.warp2 = tl.warp2;
+    L.bank_floats = tl.bank_floats; L.warp2 = tl.warp2; L.warp1 = tl.warp1;
     L.tw = pl.tw.p; L.split = pl.split.p; L.twr = pl.twr.p;
     SGX_CUDA(launch_stft(pl.cfg, L, s));
     SGX_CUDA(cudaMemcpyAsync(out, d_out.p, elems * sizeof(float), cudaMemcpyDeviceToHost, s));

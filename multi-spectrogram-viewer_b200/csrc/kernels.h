@@ -22,6 +22,7 @@ struct StftConfig {
     bool generic;          // small-F fallback kernel (one CTA per frame)
     bool fused;            // last FFT pass fused with the split: magnitudes unpadded, block-padded mel bank
     bool warp2;            // n_fft = 2048: the warp-per-frame-pair kernel (stft_warp2_kernel.cu) is preferred when its tile fits
+    bool warp1;            // n_fft = 2048: the warp-per-frame kernel on packed complex values (stft_warp1_kernel.cu), likewise
 };
 bool stft_config_for(size_t n_fft, StftConfig *cfg);
 size_t stft_max_dynamic_smem();
@@ -32,7 +33,7 @@ cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &launch, cudaStr
 // Chooses frames per tile / staging for a set of (hop) values sharing one FFT size.
 // `bank_floats`: shared-memory floats the largest mel filterbank of the launch needs (taps rounded up to 4, plus
 // 4 per filter for its descriptor), 0 when not a mel launch; the planner reports whether it got its own region.
-struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; int sample_floats; int warp2; };
+struct StftTiling { int frames_per_tile; int staged; int tile_floats; size_t smem_bytes; int bank_floats; int sample_floats; int warp2; int warp1; };
 // `sample_floats`: 2 when the launch holds f32 stereo tracks (their tiles are staged as raw interleaved pairs), else 1.
 // `warp2_ok`: every mel track of the launch has a segment-form bank (the warp kernel has no other mel path).
 StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats = 0, int sample_floats = 1, bool warp2_ok = true);
@@ -41,6 +42,10 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats =
 cudaError_t launch_stft_warp2(const StftLaunch &launch, cudaStream_t stream);
 size_t stft_warp2_fixed_smem(int bank_floats, int warps); // shared memory besides the PCM tile
 int stft_warp2_warps();                                    // warps per CTA (8 unless SGX_W2_WARPS = 10 | 12)
+// the warp-per-frame kernel on packed complex values (n_fft = 2048); `launch.warp1` routes launch_stft here
+cudaError_t launch_stft_warp1(const StftLaunch &launch, cudaStream_t stream);
+size_t stft_warp1_fixed_smem(int bank_floats, int warps);
+int stft_warp1_warps();                                    // warps per CTA (16 unless SGX_W1_WARPS = 8 | 12)
 
 // FFT twiddle tables for one size (host vectors -> caller uploads).
 void make_fft_tables(int h, float2 *tw /*[h]*/, float2 *split /*[h/2+1]*/);

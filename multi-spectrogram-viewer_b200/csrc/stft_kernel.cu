@@ -1014,6 +1014,12 @@ bool stft_config_for(size_t n_fft, StftConfig *cfg)
     // per C5 step, see its header) -- an evaluated alternative, off by default
     static const bool w2_on = getenv("SGX_K1W2") && atoi(getenv("SGX_K1W2")) == 1;
     cfg->warp2 = h == 1024 && !cfg->generic && cfg->fused && w2_on && want_pts == 0;
+    // SGX_K1W1=1: one warp per frame on packed complex values (stft_warp1_kernel.cu)
+    constexpr bool kW1Default = false;
+    static const bool block_only = getenv("SGX_K1BLOCK") && atoi(getenv("SGX_K1BLOCK")) == 1;
+    static const bool w1_on = !block_only && (getenv("SGX_K1W1") ? atoi(getenv("SGX_K1W1")) == 1 : kW1Default);
+    cfg->warp1 = h == 1024 && !cfg->generic && cfg->fused && w1_on && want_pts == 0;
+    if (cfg->warp1 || block_only) cfg->warp2 = false;
     return true;
 }
 
@@ -1029,6 +1035,24 @@ StftTiling plan_stft_tiles(const StftConfig &cfg, int max_hop, int bank_floats, 
     }
     int want_nfr = 0;
     if (const char *e = getenv("SGX_K1_NFR")) want_nfr = atoi(e);
+    if (cfg.warp1 && warp2_ok) {
+        // one frame per warp and round; the tile gets what the exchange planes, tables and filterbank leave
+        const int nw = stft_warp1_warps();
+        const size_t fixed = stft_warp1_fixed_smem(bank_floats, nw);
+        const long cap_floats = stft_max_dynamic_smem() > fixed ? (long)((stft_max_dynamic_smem() - fixed) / sizeof(float)) : 0;
+        int best = 0;
+        for (int mult = 1; mult <= 4; ++mult) {
+            const int nfr = nw * mult;
+            const long need = 3 + (long)(nfr - 1) * max_hop + cfg.n_fft + 4;
+            if (need <= cap_floats && (nfr <= (want_nfr ? want_nfr : 2 * nw) || best == 0)) best = nfr;
+        }
+        if (best > 0) {
+            t.frames_per_tile = best; t.staged = 1; t.warp1 = nw; t.bank_floats = bank_floats; t.sample_floats = 1;
+            t.tile_floats = (int)((3 + (long)(best - 1) * max_hop + cfg.n_fft + 3) & ~3L) + 4;
+            t.smem_bytes = fixed + (size_t)t.tile_floats * sizeof(float);
+            return t;
+        }
+    }
     if (cfg.warp2 && warp2_ok) {
         // eight warps x two frames per round; the tile gets what the exchange planes, tables and filterbank leave
         const int nw = stft_warp2_warps();
@@ -1120,6 +1144,7 @@ void make_fft_tables(int h, float2 *tw, float2 *split)
 cudaError_t launch_stft(const StftConfig &cfg, const StftLaunch &L, cudaStream_t stream)
 {
     if (L.n_tiles <= 0) return cudaSuccess;
+    if (L.warp1) return launch_stft_warp1(L, stream);
     if (L.warp2) return launch_stft_warp2(L, stream);
     const size_t smem = cfg.generic ? cfg.fft_smem
                                     : 16 + (size_t)(L.tile_floats + L.bank_floats) * sizeof(float) + cfg.fft_smem;

@@ -209,10 +209,12 @@ print("K3 AB OK", len(out))
         assert a.shape == b.shape and np.array_equal(a, b), f"{k}: {int((a != b).sum())} of {a.size} bytes differ"
 
 
-def test_warp_pair_kernel_at_n_fft_2048_parity(orc):
-    """n_fft = 2048 has two kernels: the block kernel (default, exercised by every other test) and the
-    warp-per-frame-pair one (SGX_K1W2=1, csrc/stft_warp2_kernel.cu).  The alternative must meet the same
-    tolerances; the choice is made per process, so it runs in a child interpreter."""
+@pytest.mark.parametrize("flag", ["SGX_K1W2", "SGX_K1W1", "SGX_K1BLOCK"])
+def test_every_kernel_for_n_fft_2048_meets_parity(orc, flag):
+    """n_fft = 2048 has three kernels: the block kernel (csrc/stft_kernel.cu), the warp-per-frame-pair one (SGX_K1W2=1,
+    csrc/stft_warp2_kernel.cu) and the warp-per-frame one on packed complex values (SGX_K1W1=1, csrc/stft_warp1_kernel.cu).
+    Whichever is the default is exercised by every other test; each must meet the same tolerances.  The choice is made
+    per process, so they run in child interpreters (SGX_K1BLOCK=1 forces the block kernel)."""
     import subprocess
     import sys
     import os
@@ -234,10 +236,25 @@ assert_db_close(msv.melspectrogram_db(x, 2048, 512, 2048), orc.calc_spec(x, 2048
 y = synth.base_clip(2 * 44100, 44100, 6)  # odd hop 441: unaligned frame starts
 fb = msv.calc_mel_fb_default(44100, 2048)
 assert_db_close(msv.melspectrogram_db(y, 1764, 441, 2048, None, fb), orc.calc_spec(y, 1764, 441, 2048, None, fb), "K1 W2 44.1k")
+# the whole path on a stereo int16 track and a mono f32 one (gathered and TMA-staged tiles), pixels against the oracle
+from parity import assert_pixels_close, assert_range_close
+srs = [48000, 48000]
+wavs = [synth.derive_track(synth.base_clip(5 * 48000 + 123, 48000, seed=11), 0), synth.derive_track(synth.base_clip(4 * 48000 + 7, 48000, seed=12), 1)]
+params = [orc.track_params(sr) for sr in srs]
+fbs = [orc.calc_mel_fb_default(sr, p[2]) for sr, p in zip(srs, params)]
+wins = [orc.calc_window(p[0], p[2]) for p in params]
+imgs, mx, mn = orc.pipeline(wavs, srs, params, wins, fbs, channels=4, px_per_sec=100.0, nheight=500)
+mt = msv.MultiTrack()
+mt.add_tracks_pcm([0, 1], wavs, srs)
+assert_range_close((mt.get_max_db(), mt.get_min_db()), (mx, mn), what="range")
+for i, g in enumerate(mt.get_spec_images([0, 1], 100.0, 500, 4)):
+    assert_pixels_close(g.reshape(imgs[i].shape), imgs[i], f"track {i}")
+mt.close()
 print("K1 W2 OK")
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SGX_K1W2="1")
+    env = dict(os.environ, SGX_K1W2="0", SGX_K1W1="0")
+    env[flag] = "1"
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "K1 W2 OK" in r.stdout, r.stdout + r.stderr
 
