@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, step K: sliding-window render kernel -- GPU suite, then C5 / C3 / C4 / C2 with the kernel on and off
+# sliding-window render kernel (default) against render_fast_kernel (SGX_K3_SLIDE=0): GPU suite, C5 / C3 / C2 / C1
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 grep -E "passed|failed|pytest exit|AssertionError:|Error" gpurun_out/pytest_gpu.log | tail -12
@@ -16,10 +16,7 @@ except Exception as ex:
 PY
 }
 run "c5 slide" SGX_K3_SLIDE=1 --workload c5
-run "c5 fast" SGX_K3_SLIDE=0 --workload c5
 run "c3 slide" SGX_K3_SLIDE=1 --workload c3
-run "c3 fast" SGX_K3_SLIDE=0 --workload c3
-run "c4_16384 slide" SGX_K3_SLIDE=1 --workload c4 --n-fft 16384 --tracks 4
-run "c4_16384 fast" SGX_K3_SLIDE=0 --workload c4 --n-fft 16384 --tracks 4
+run "c5 fast" SGX_K3_SLIDE=0 --workload c5
 run "c2 slide" SGX_K3_SLIDE=1 --workload c2
-run "c2 fast" SGX_K3_SLIDE=0 --workload c2
+run "c1 slide" SGX_K3_SLIDE=1 --workload c1
