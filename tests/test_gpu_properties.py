@@ -168,8 +168,9 @@ def test_sliding_window_render_kernel_matches_the_tile_kernel_bit_for_bit():
     csrc/render_slide_kernel.cu) and render_fast_kernel (SGX_K3_SLIDE=0).  They apply the same operations in the same
     order, so every pixel must be IDENTICAL -- over RGB and RGBA, widths that are and are not multiples of 4 (128-bit
     and scalar store paths), horizontal ratios at and below 1 (unit-step and general column blocks), heights that
-    are not a multiple of the tile, and several sample rates in one call (one launch over mixed geometries).  The kernel
-    is chosen per process, so both run in children."""
+    are not a multiple of the tile, several sample rates in one call (one launch over mixed geometries), and one
+    10-minute track at the bench geometry (compared by digest).  The kernel is chosen per process, so both run in
+    children."""
     import os
     import subprocess
     import sys
@@ -188,7 +189,17 @@ for ch in (3, 4):
     for pps, nh in ((100.0, 500), (100.0, 333), (173.0, 257), (250.0, 64), (97.0, 1000)):
         for i, g in enumerate(mt.get_spec_images(list(range(len(srs))), pps, nh, ch)):
             out[f"{ch}_{pps}_{nh}_{i}"] = np.asarray(g).copy()
-n1 = msv.kernel_launch_count()
+mt.close()
+# the bench geometry at FULL size (BASELINE C5: 10 minutes at 48 kHz -> 60,001 frames -> 60,000 x 500 RGBA): the tile
+# capacity of the sliding-window kernel is exact for it (127 or 128 source frames per 120 columns, never 129)
+import hashlib
+x = synth.base_clip(600 * 48000, 48000, seed=99)
+mt = msv.MultiTrack()
+mt.add_tracks_pcm([0], [x], [48000])
+img = np.asarray(mt.get_spec_images([0], 100.0, 500, 4)[0])
+assert img.size == 60000 * 500 * 4
+out["c5_full_sha256"] = np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8).copy()
+out["c5_full_mean"] = np.array([img.mean()])
 mt.close()
 np.savez(sys.argv[1], **out)
 print("K3 AB OK", len(out))
@@ -203,7 +214,7 @@ print("K3 AB OK", len(out))
             assert r.returncode == 0 and "K3 AB OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
             with np.load(path) as z:
                 got[name] = {k: z[k] for k in z.files}
-    assert got["slide"].keys() == got["tile"].keys() and len(got["slide"]) == 50
+    assert got["slide"].keys() == got["tile"].keys() and len(got["slide"]) == 52
     for k in got["slide"]:
         a, b = got["slide"][k], got["tile"][k]
         assert a.shape == b.shape and np.array_equal(a, b), f"{k}: {int((a != b).sum())} of {a.size} bytes differ"
