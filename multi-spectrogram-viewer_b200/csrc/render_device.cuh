@@ -40,32 +40,12 @@ __device__ __forceinline__ unsigned grey_to_rgba_const(float x)
     return fl < 9.0f ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
 }
 
-// The same function without conversion instructions (F2I / FRND run on the quarter-rate XU pipe: five per pixel were
-// 1.0 ms of XU time per C5 step).  For 0 <= v < 2^23, v + 2^23 rounded towards minus infinity is 2^23 + floor(v) exactly,
-// so the integer sits in the low mantissa bits: floor(position) for the segment index (position <= ~12) and the three
-// channel bytes.  Bit-identical to grey_to_rgba_const for every finite x >= 0 (tools/check_colormap_fadd.cpp).
-__device__ __forceinline__ unsigned grey_to_rgba_fadd(float x)
-{
-    const float kMagic = 8388608.0f; // 2^23
-    const float position = __fmul_rn(10.0f, fminf(x, 1.5f)); // x >= 1 is the last colour already; keeps position < 16
-    const float tf = __fadd_rd(position, kMagic);
-    const unsigned ti = __float_as_uint(tf) & 0xfu;       // floor(position), 0 .. 15
-    const float fl = __fsub_rn(tf, kMagic);               // exact
-    const int idx = min((int)ti, 8);
-    const float ratio = __fsub_rn(position, fl);
-    const float4 rg = kCmConst[idx].rg;
-    const float4 b = kCmConst[idx].b;
-    const unsigned cr = __float_as_uint(__fadd_rd(fmaf(ratio, rg.y, rg.x), kMagic));
-    const unsigned cg = __float_as_uint(__fadd_rd(fmaf(ratio, rg.w, rg.z), kMagic));
-    const unsigned cb = __float_as_uint(__fadd_rd(fmaf(ratio, b.y, b.x), kMagic));
-    // bytes: [0] = cr.b0, [1] = cg.b0, [2] = cb.b0, [3] = 0xff
-    const unsigned px = __byte_perm(__byte_perm(cr, cg, 0x0040), cb, 0x7410) | 0xff000000u;
-    return ti < 9u ? px : 0xffa4fffcu; // index >= len-1 -> (252, 255, 164)
-}
-
-// The leanest form, used by the sliding-window kernel.  With position = i + ratio (ratio = position - floor(position) is
-// exact in f32), ratio * d + (a + 0.5) and position * d + (a + 0.5 - i d) are the SAME real number, and a + 0.5 - i d
-// is a small multiple of 0.5, exact in f32: one FMA per channel straight from `position`, bit-identical to the two forms
+// The sliding-window kernel computes the same function without conversion instructions (F2I / FRND run on the quarter-rate
+// XU pipe: five per pixel were 1.0 ms of XU time per C5 step).  For 0 <= v < 2^23, v + 2^23 rounded towards minus infinity
+// (FADD.RM) is 2^23 + floor(v) exactly, so the integer sits in the low mantissa bits: floor(position) for the segment
+// index and the three channel bytes.  And with position = i + ratio (ratio = position - floor(position) is exact in
+// f32), ratio * d + (a + 0.5) and position * d + (a + 0.5 - i d) are the SAME real number, and a + 0.5 - i d
+// is a small multiple of 0.5, exact in f32: one FMA per channel straight from `position`, bit-identical to the form
 // above, with neither floor nor ratio computed.  A tenth table entry (d = 0) returns the last colour for position >= 9.
 struct CmPos { float4 rg, b; };
 __constant__ CmPos kCmPos[10] = {
@@ -80,25 +60,13 @@ __constant__ CmPos kCmPos[10] = {
 };
 // t: the un-clamped sum of the last resampling pass.  __saturatef is the clamp at 0 of image's resize; values above 1
 // all map to the last colour, as do 1 and everything from 0.9 on (display.rs:31), so clipping them to 1 changes nothing.
-__device__ __forceinline__ unsigned grey_to_rgba_sat(float t)
-{
-    const float kMagic = 8388608.0f; // 2^23
-    const float position = __fmul_rn(10.0f, __saturatef(t)); // <= 10
-    const unsigned ti = __float_as_uint(__fadd_rd(position, kMagic)) & 0xfu; // floor(position), 0 .. 15
-    const int idx = min((int)ti, 9);
-    const float4 rg = kCmPos[idx].rg;
-    const float4 b = kCmPos[idx].b;
-    const unsigned cr = __float_as_uint(__fadd_rd(fmaf(position, rg.y, rg.x), kMagic));
-    const unsigned cg = __float_as_uint(__fadd_rd(fmaf(position, rg.w, rg.z), kMagic));
-    const unsigned cb = __float_as_uint(__fadd_rd(fmaf(position, b.y, b.x), kMagic));
-    return __byte_perm(__byte_perm(cr, cg, 0x0040), cb, 0x7410) | 0xff000000u; // [0] = cr.b0, [1] = cg.b0, [2] = cb.b0, [3] = 0xff
-}
-
-// grey_to_rgba_sat for a lane that walks along an image row: neighbouring pixels mostly fall into the same colour segment,
+// Bit-identical to grey_to_rgba_const(clamp(t)) for every float (tools/check_colormap_fadd.cpp: every value in [0, 2]).
+// The lane that calls it walks along an image row: neighbouring pixels mostly fall into the same colour segment,
 // so the segment's six constants stay in registers and are re-loaded (predicated, per lane) only when the segment
 // changes.  An indexed constant load costs one request per DISTINCT index among the lanes that execute it: with the
-// lanes of a warp on 32 different rows that was ~3 requests per load and pixel, and the indexed constant cache bounded the
-// colour phase (ncu: idc request cycles ~100 % during it); lanes whose segment did not change make no request.
+// lanes of a warp on 32 different rows that was ~3 requests per load and pixel (ncu: the indexed constant cache busy for
+// half of the kernel's time); lanes whose segment did not change make no request.  Measured effect on the kernel time:
+// none (3.55 -> 3.54 ms per C5 step) -- it was not the limiter; kept because it costs nothing.
 struct CmCache { float4 rg; float2 b; int idx; };
 __device__ __forceinline__ void cm_cache_init(CmCache &c) { c.idx = -1; c.rg = make_float4(0.f, 0.f, 0.f, 0.f); c.b = make_float2(0.f, 0.f); }
 __device__ __forceinline__ unsigned grey_to_rgba_cached(float t, CmCache &c)

@@ -1,5 +1,5 @@
 // check_colormap_fadd.cpp -- host check that the conversion-free colour map of csrc/render_device.cuh
-// (grey_to_rgba_fadd: floor taken from the mantissa of v + 2^23 rounded down; grey_to_rgba_pos: the FMAs
+// (floor taken from the mantissa of v + 2^23 rounded down -- `fast` below; grey_to_rgba_cached: in addition the FMAs
 // straight from `position`) return the bytes of grey_to_rgba_const
 // for EVERY float x in [0, 2] (and a few beyond).  Build and run:  g++ -O1 -frounding-math -o /tmp/ccf tools/check_colormap_fadd.cpp && /tmp/ccf
 #include <cfenv>
