@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(kSlThreads, 3) render_slide_kernel(const Rende
         // segments of 32 bytes.  (Two 128-bit stores per lane straight from registers, 32 rows apart, measured slower.)
         unsigned *stage = reinterpret_cast<unsigned *>(G) + warp * (8 * kSlSP);
         unsigned char *__restrict__ outp = tr->out;
-        const bool wide = CH == 4 && (ox_count & 3) == 0 && (reinterpret_cast<size_t>(outp) & 15) == 0; // x0 is a multiple of 8
+        // x0 is a multiple of 8 pixels by construction: four RGBA pixels are 16 aligned bytes, four RGB pixels 12 bytes on a 4-byte boundary
+        const bool wide = (ox_count & 3) == 0 && (reinterpret_cast<size_t>(outp) & (CH == 4 ? 15 : 3)) == 0;
         unsigned *sa = stage + lane, *sb = sa + 32;
         const float *__restrict__ ta = Tm + min(lane, pyc - 1);
         const float *__restrict__ tb = Tm + min(lane + 32, pyc - 1);
@@ -313,10 +314,20 @@ __global__ void __launch_bounds__(kSlThreads, 3) render_slide_kernel(const Rende
                     const unsigned *sp = stage + (lane & 1) * (4 * kSlSP) + (lane >> 1);
                     unsigned char *dst = outp + ((size_t)(oy0 + (lane >> 1)) * ox_count + x0 + 4 * (lane & 1)) * 4;
                     const size_t dstep = (size_t)16 * ox_count * 4;
+                    unsigned char *dst3 = outp + ((size_t)(oy0 + (lane >> 1)) * ox_count + x0 + 4 * (lane & 1)) * 3;
+                    const size_t dstep3 = (size_t)16 * ox_count * 3;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) { // rows 16 g + lane / 2, columns 4 (lane & 1) .. + 3
                         const unsigned p0 = sp[16 * g], p1 = sp[16 * g + kSlSP], p2 = sp[16 * g + 2 * kSlSP], p3 = sp[16 * g + 3 * kSlSP];
-                        if (16 * g + (lane >> 1) < pyc) st_global_v4(dst + g * dstep, p0, p1, p2, p3);
+                        if (16 * g + (lane >> 1) < pyc) {
+                            if (CH == 4) st_global_v4(dst + g * dstep, p0, p1, p2, p3);
+                            else { // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3  (the reference's RGB layout, lib.rs:294-298)
+                                unsigned char *d3 = dst3 + g * dstep3;
+                                st_global_u32(d3, __byte_perm(p0, p1, 0x4210));
+                                st_global_u32(d3 + 4, __byte_perm(p1, p2, 0x5421));
+                                st_global_u32(d3 + 8, __byte_perm(p2, p3, 0x6542));
+                            }
+                        }
                     }
                 } else {
                     const int sub_r = lane >> 3, sub_c = lane & 7;
